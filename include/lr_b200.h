@@ -1,0 +1,188 @@
+/*
+ * lr_b200.h — C ABI of liblr_b200.so, the B200 (sm_100a) retrieval hot path.
+ *
+ * The reference (caskcsg/lightretriever) has no FFI of its own: the seams are
+ * Python duck-typed protocols.  Every entry point below names the reference
+ * interface (file:line under /root/reference) whose arithmetic it replaces.
+ * A maintainer binds these with ctypes; torch is only the
+ * allocator — every argument is a plain device pointer, a size, or a stream.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns LR_OK (0) or a negative LR_E* code; the message is
+ *     available from lr_last_error() (thread-local);
+ *   - nothing is allocated by the library: the caller owns outputs and the
+ *     workspace (size it with the *_workspace_bytes functions);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns LR_ECUDA.
+ */
+#ifndef LR_B200_H
+#define LR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LR_OK        0
+#define LR_EINVAL   -1   /* bad shape / dtype / alignment  -> Python ValueError   */
+#define LR_ECUDA    -2   /* CUDA runtime / driver failure  -> Python RuntimeError */
+#define LR_EWORKSPACE -3 /* workspace too small            -> Python ValueError   */
+
+/* dtype tags */
+#define LR_F32  0
+#define LR_BF16 1
+
+/* score kinds carried in the high word of a 64-bit candidate key */
+#define LR_SCORE_F32 0   /* order-preserving map of an IEEE float (dense path) */
+#define LR_SCORE_U32 1   /* non-negative integer impact score (sparse path)     */
+
+const char* lr_last_error(void);
+int         lr_version(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int         lr_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  EmbeddingBag query encoder (mean, padding_idx) + MRL truncate + L2 norm
+ *   replaces  emb_bag.forward(input, offsets)   finetune/modeling_hybrid.py:474
+ *             emb_reps[..., :dense_shrink_dim]  finetune/modeling_hybrid.py:487-488
+ *             F.normalize(emb_reps, p=2, dim=-1) finetune/modeling_hybrid.py:489-490
+ *   ids      [n_ids]  int64, flattened token ids (nonctx_emb_utils.py:197-219)
+ *   offsets  [n_bags] int64, bag starts; last bag runs to n_ids
+ *            (torch include_last_offset=False)
+ *   table    [V, d] row-major, table_dtype LR_BF16 | LR_F32, rows 16-byte aligned
+ *   padding_idx  id excluded from sum and from the mean's denominator; -1 = none
+ *   out_dim  m <= d, m % 8 == 0 : only the first m columns are read and written
+ *   normalize != 0 : x / max(||x||_2, 1e-12)
+ *   out      [n_bags, out_dim] out_dtype LR_BF16 | LR_F32
+ * Empty bag (or all-padding bag) -> zero vector (torch semantics).
+ * An id outside [0, V) is an error in torch; here it sets the row to NaN and the
+ * call returns LR_EINVAL after the kernel (checked through a device flag).
+ * ------------------------------------------------------------------------- */
+int lr_embbag_encode(const int64_t* ids, const int64_t* offsets, int64_t n_ids, int64_t n_bags,
+                     const void* table, int table_dtype, int64_t V, int64_t d, int64_t padding_idx,
+                     int64_t out_dim, int normalize, void* out, int out_dtype,
+                     int32_t* err_flag /* device int32, may be NULL */, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K1b  document dense head: last-token pooling + truncate + normalise
+ *   replaces pooling(last_hidden, attention_mask, 'lasttoken')  finetune/dense_pooling.py:48-55
+ *            + shrink / normalize                               finetune/modeling_hybrid.py:266-278
+ *   hidden [B, S, d] (dtype LR_BF16 | LR_F32); mask [B, S] int64 (HF attention mask)
+ *   If every row's last column is valid (left padding) row S-1 is taken for all
+ *   rows, else row sum(mask)-1 (negative index wraps like torch: -1 -> S-1).
+ *   scratch: device int32[B + 1].
+ * ------------------------------------------------------------------------- */
+int lr_lasttoken_head(const void* hidden, int hidden_dtype, const int64_t* mask,
+                      int64_t B, int64_t S, int64_t d, int64_t out_dim, int normalize,
+                      void* out, int out_dtype, int32_t* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2  exact flat inner-product top-k   (TMA -> tcgen05.mma -> TMEM -> top-k epilogue)
+ *   replaces FaissIndex.search(q, k) -> (scores f32 [Q,k] desc, ids i64 [Q,k])
+ *            retriever/faiss_index.py:27-40 (faiss.IndexFlatIP.search), and the
+ *            per-chunk heap merge retriever/hybrid_search.py:182-205.
+ *   q       [Q, ldq]  bf16, row-major, ldq*2 % 16 == 0, base 16-byte aligned
+ *   corpus  [N, ldc]  bf16, row-major, ldc*2 % 16 == 0, base 16-byte aligned
+ *   d_used  inner-product length (MRL prefix m <= ldq, ldc); % 8 == 0
+ *   q_scale [Q] / c_scale [N] f32 or NULL: score = dot * q_scale[q] * c_scale[n]
+ *           (MRL on full-width stored vectors: reciprocal prefix norms)
+ *   id_offset  added to the local row index (row-sharded corpus); ids must stay < 2^32
+ *   k       1 <= k <= 2048
+ *   out_scores [Q,k] f32 descending; out_ids [Q,k] i64; when N < k the tail is
+ *   (-inf, -1) (Faiss convention for missing results).
+ *   out_keys   optional [Q,k] u64 sorted candidate keys (for the cross-GPU merge), may be NULL
+ *   Ties: equal scores are ordered by ascending id (Faiss leaves this undefined).
+ *   workspace: >= lr_flatip_workspace_bytes(Q, N, k) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------- */
+size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k);
+int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
+                   int64_t Q, int64_t N, int64_t d_used,
+                   const float* q_scale, const float* c_scale, int64_t id_offset, int k,
+                   float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                   void* workspace, size_t ws_bytes, void* stream);
+
+/* Debug / parity helper: the same TMA+tcgen05 main loop with a plain store
+ * epilogue, scores [Q, N] f32 (small shapes only). Definition of the score:
+ * torch.matmul(q, p.T)  finetune/modeling_encoder.py:414-427. */
+int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
+                     int64_t Q, int64_t N, int64_t d_used, float* out_scores /*[Q,N]*/, void* stream);
+
+/* Plan of the last lr_flatip_topk call on this thread (for bench / DESIGN):
+ * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=rounds */
+int lr_flatip_last_plan(int64_t* out8);
+
+/* ---------------------------------------------------------------------------
+ * Merge of candidate lists (per-split partials, per-shard top-k after the
+ * NCCL all-gather, per-chunk results):  exact top-k of the union.
+ *   replaces HybridSearch._add_to_heap  retriever/hybrid_search.py:182-205
+ *            (and Faiss IndexShards' host-side merge, retriever/faiss_index.py:65-68)
+ *   keys    L lists per query; list l of query q starts at keys[(l*q_stride + q)*cap]
+ *   counts  [L*q_stride] int32 valid entries per list, or NULL = every list holds `cap`
+ *   key     = (score_key << 32) | (0xFFFFFFFF - id32); keys equal to 0 are ignored
+ *   outputs any of out_scores/out_ids/out_keys may be NULL; sorted (score desc, id asc)
+ * ------------------------------------------------------------------------- */
+int lr_topk_merge(const uint64_t* keys, const int32_t* counts, int L, int64_t Q, int64_t q_stride,
+                  int cap, int k, int score_kind, int64_t id_offset,
+                  float* out_scores, int64_t* out_ids, uint64_t* out_keys, void* stream);
+
+/* (scores f32, ids i64) [n] -> candidate keys u64 [n]; id < 0 -> key 0 (ignored). */
+int lr_encode_keys(const float* scores, const int64_t* ids, int64_t n, uint64_t* keys, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K3  document sparse head
+ *   replaces aggregate()/max_linear_mapping  finetune/sparse_pooling.py:244-278,
+ *            utils/max_linear_map.py:10-90  (max over valid tokens of h_t.W + b)
+ *            relu_/log1p_                   finetune/modeling_hybrid.py:183-187
+ *   hidden [B*S, d] bf16 (tokens of doc b are rows b*S .. b*S+S-1), W [V, d] bf16
+ *   (= lm_head.weight), bias [V] f32 or NULL, mask [B*S] uint8 (1 = valid token;
+ *   get_sparse_attention_mask, finetune/sparse_pooling.py:23-41)
+ *   out [B, V] f32:  max_t(h_t.W_v + b_v) over valid t, then optional relu, log1p.
+ *   A doc without valid token gives finfo(bf16).min before relu (max_linear_map.py:27).
+ * ------------------------------------------------------------------------- */
+int lr_sparse_head_max(const void* hidden, const void* W, const float* bias, const uint8_t* mask,
+                       int64_t B, int64_t S, int64_t d, int64_t V, int relu, int log1p,
+                       float* out /*[B,V]*/, void* stream);
+
+/* top_k_sampling (finetune/sparse_pooling.py:89-106: keep every entry >= the k_eff-th
+ * largest, k_eff = min(max(top_k, min_keep), V), top_k <= 0 disables) followed by the
+ * quantiser of convert_sparse_reps_to_json_pt (finetune/sparse_converter_mixin.py:103-160):
+ * clamp(min=0), round-half-even(x*quant) -> int, zeros dropped.
+ *   reps [B, V] f32 ; indptr [B+1] int32 ; tok/impact [cap] ; returns LR_EWORKSPACE
+ *   if nnz > cap (indptr is still fully written so the caller can re-size).
+ *   scratch: device, >= lr_sparsify_scratch_bytes(B, V). */
+size_t lr_sparsify_scratch_bytes(int64_t B, int64_t V);
+int lr_sparsify_quantize(const float* reps, int64_t B, int64_t V, int top_k, int min_keep, float quant,
+                         int32_t* indptr, int32_t* tok, uint16_t* impact, int64_t cap,
+                         void* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  sparse impact scoring + top-k over an inverted index (CSC by token)
+ *   replaces Anserini impact search  retriever/anserini_search.py:143-216
+ *   score(q,d) = sum_t count_q(t) * impact_d(t)   scripts/asymmetric_sparse_infer.ipynb:207-228
+ *   q_indptr [Q+1] i32, q_tok [nnz_q] i32, q_cnt [nnz_q] i32   (Counter(ids), exact_search_base.py:371-435)
+ *   post_indptr [V+1] i64, post_doc [nnz] i32 ascending inside a token, post_imp [nnz] u16
+ *   Only documents with score > 0 are returned (Lucene returns matching docs only);
+ *   missing tail = (-inf, -1). Scores are exact integers (returned as f32; exact < 2^24).
+ * ------------------------------------------------------------------------- */
+/* Documents are scored in blocks of lr_sparse_block_docs() (16384) consecutive ids whose int32 accumulators
+ * live in shared memory.  blockptr[t*(nblk+1) + b] = number of postings of token t with doc < b*block_docs
+ * (nblk = ceil(N / block_docs)); built once per index (index time, not on the query path). */
+int    lr_sparse_block_docs(void);
+int    lr_sparse_build_blockptr(const int64_t* post_indptr, const int32_t* post_doc, int64_t V, int64_t N,
+                                uint32_t* blockptr /* [V*(nblk+1)] */, void* stream);
+size_t lr_sparse_score_workspace_bytes(int64_t Q, int64_t N, int k);
+/* k <= 1024 */
+int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_tok, const int32_t* q_cnt, int64_t Q,
+                         const int64_t* post_indptr, const int32_t* post_doc, const uint16_t* post_imp,
+                         const uint32_t* blockptr, int64_t V, int64_t N, int64_t id_offset, int k,
+                         float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                         void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LR_B200_H */

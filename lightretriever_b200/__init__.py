@@ -1,0 +1,15 @@
+"""lightretriever_b200 — B200-native serving-side retrieval hot path of caskcsg/lightretriever.
+
+Hand-written sm_100a CUDA kernels (csrc/) behind a C ABI (include/lr_b200.h, liblr_b200.so), driven by a thin Python
+host layer that keeps the reference's encode / index / retrieve_with_emb / search interfaces.  No CPU fallback.
+"""
+from . import _C  # noqa: F401  (ctypes binding; `_C.load()` builds/loads liblr_b200.so)
+from .encode import B200EmbeddingBag, flatten_token_ids, lasttoken_head, tokenize_nonctx_qry_emb_bag
+from .search import FlatIPIndex, FlatIPSearch, encode_keys, flatip_scores, flatip_topk, topk_merge
+from .sharded import ShardedFlatIPIndex, exchange_candidates, shard_range
+from .sparse_head import (aggregate, convert_sparse_reps_to_json, csr_to_json, get_sparse_attention_mask,
+                          max_linear_mapping, sparse_head, sparsify_quantize)
+from .sparse_search import ImpactIndex, ImpactSearch
+from .hybrid import HybridSearch, fuse_scores_linear, fuse_scores_rrf
+
+__version__ = "0.1.0"

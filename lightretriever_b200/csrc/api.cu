@@ -1,0 +1,48 @@
+// api.cu — error reporting and device queries of the C ABI (include/lr_b200.h).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace lr {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return 148;  // B200; only reached on a box without a CUDA device (workspace sizing in CPU tests)
+  }
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 148;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace lr
+
+extern "C" const char* lr_last_error(void) { return lr::g_err; }
+extern "C" int lr_version(void) { return 100; }
+extern "C" int lr_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    lr::set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return LR_ECUDA;
+  }
+  return n;
+}

@@ -1,0 +1,266 @@
+// common.cuh — error plumbing, key encoding and sm_100a PTX wrappers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/lr_b200.h"
+
+namespace lr {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define LR_CHECK_ARG(cond, ...)                         \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      lr::set_error(__VA_ARGS__);                       \
+      return LR_EINVAL;                                 \
+    }                                                   \
+  } while (0)
+#define LR_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      lr::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return LR_ECUDA;                                                             \
+    }                                                                              \
+  } while (0)
+#define LR_LAUNCH_CHECK()                                                          \
+  do {                                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      lr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return LR_ECUDA;                                                             \
+    }                                                                              \
+  } while (0)
+
+int sm_count();  // cached per device
+
+// ---------------------------------------------------------------- candidate keys
+// A candidate is one u64: high word = order-preserving image of the score, low word =
+// 0xFFFFFFFF - id, so that an unsigned descending sort yields (score desc, id asc).
+__host__ __device__ __forceinline__ uint32_t f32_to_key(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f + 0.0f);  // -0 -> +0
+#else
+  float g = f + 0.0f;
+  uint32_t u;
+  memcpy(&u, &g, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_to_f32(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(uint32_t score_key, uint32_t id) {
+  return (uint64_t(score_key) << 32) | uint64_t(0xFFFFFFFFu - id);
+}
+__host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return 0xFFFFFFFFu - uint32_t(k); }
+__host__ __device__ __forceinline__ uint32_t key_hi(uint64_t k) { return uint32_t(k >> 32); }
+constexpr uint32_t KEY_NEG_INF = 0x007FFFFFu;  // f32_to_key(-inf)
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- cache-hinted global access
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_cg_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------- shared / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+#ifndef LR_MBAR_TIMEOUT_CYCLES
+#define LR_MBAR_TIMEOUT_CYCLES (20ll * 1000 * 1000 * 1000)
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > LR_MBAR_TIMEOUT_CYCLES) {
+      printf("lr_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- TMA
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// createpolicy constants (same encodings CUTLASS uses for TMA::CacheHintSm90)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST  = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST   = 0x14F0000000000000ull;
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> f32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive f32 columns: thread i of the warp receives lane (taddr.lane + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups of 1024 bytes).
+// Bit layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout_type [61,64) with SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return uint64_t((smem_addr >> 4) & 0x3FFFu) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// kind::f16 instruction descriptor: f32 accumulate, bf16 A/B, both K-major (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// One warp scans a 256-bin histogram from the top bin down and finds the bin holding the `remaining`-th
+// largest element.  Returns (bin, rank inside the bin, whether the bin is taken whole) in every lane.
+__device__ __forceinline__ void warp_find_bin_desc(const uint32_t* hist, uint32_t remaining, uint32_t& bin,
+                                                   uint32_t& rem2, bool& take_all) {
+  const uint32_t full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int base = 8 * (31 - lane);  // lane 0 owns the highest bins
+  uint32_t c[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i] = hist[base + 7 - i];
+    sum += c[i];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t t = __shfl_up_sync(full, incl, off);
+    if (lane >= off) incl += t;
+  }
+  const uint32_t excl = incl - sum;
+  const bool hit = (excl < remaining) && (remaining <= incl);
+  const uint32_t hm = __ballot_sync(full, hit);
+  const int src = hm ? (__ffs(hm) - 1) : 31;
+  uint32_t b = 0, r = 1, ta = 0;
+  if (lane == src) {
+    uint32_t acc = excl;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!done && acc + c[i] >= remaining) {
+        b = uint32_t(base + 7 - i);
+        r = remaining - acc;
+        ta = (c[i] == r) ? 1u : 0u;
+        done = true;
+      }
+      if (!done) acc += c[i];
+    }
+  }
+  bin = __shfl_sync(full, b, src);
+  rem2 = __shfl_sync(full, r, src);
+  take_all = __shfl_sync(full, ta, src) != 0;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+#endif  // __CUDACC__
+
+}  // namespace lr

@@ -1,0 +1,497 @@
+// umma_gemm.cuh — the TMA -> tcgen05.mma -> TMEM main loop shared by K2 (flat inner-product top-k) and
+// K3 (document sparse head), with the epilogue that makes each of them a fused kernel.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4-stage ring)
+//   warp 1      MMA issuer     (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: one accumulator row per thread)
+// The 128x256 f32 accumulator lives in TMEM, double buffered (2 x 256 columns), so the epilogue of
+// tile i overlaps the MMAs of tile i+1.  D = A . B^T with A = [rows, K] and B = [cols, K], both K-major bf16.
+//
+// Work decomposition: unit = (row tile of 128 rows, column split).  Units are ordered
+// (band of row tiles, split, row tile in band) and dealt round-robin to the CTAs, so the CTAs running
+// concurrently share `band` row tiles (L2-resident) and stream the same few column splits in lock step
+// (each B tile is fetched from HBM once per band and hit in L2 by the other CTAs of the band).
+//
+// Epilogues
+//   EPI_STORE   plain f32 store of the tile (debug / parity of the main loop)
+//   EPI_TOPK    K2: rows = queries, columns = documents.  Every thread compares its row's scores with a
+//               running threshold and appends the survivors to a per-(split,query) candidate list; a full
+//               list is cut back to its exact top-k by a warp-cooperative radix select.  The score matrix
+//               never reaches HBM.
+//   EPI_MAXTOK  K3: rows = vocabulary entries, columns = document tokens.  Every thread keeps the running
+//               masked max over the tokens of the current document and writes relu/log1p of it when the
+//               document ends (max_linear_map.py:72-85 + modeling_hybrid.py:183-187 in one pass).
+#pragma once
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <mutex>
+
+namespace lr {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STAGES = 2;
+constexpr int SMEM_BAR_BYTES = 256;
+constexpr int SMEM_HIST_BYTES = 4 * 256 * 4;
+constexpr int GEMM_SMEM_TOTAL = 1024 + STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES;
+
+enum { EPI_STORE = 0, EPI_TOPK = 1, EPI_MAXTOK = 2 };
+
+struct GemmParams {
+  int64_t rows, cols, row_pad;  // rows of A (queries / vocab), rows of B (documents / tokens)
+  int kblocks;
+  int m_tiles, splits, band_size, n_bands, units;
+  // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
+  int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range
+  int64_t seg_len;      // EPI_MAXTOK: tokens per document (S); split = segs_per_split documents
+  int64_t n_segs;
+  int segs_per_split;
+  // EPI_TOPK
+  int k, cap;
+  const float* q_scale;
+  const float* c_scale;
+  uint64_t* cand;    // [splits][row_pad][cap]
+  int32_t* counts;   // [splits][row_pad]
+  uint32_t* gthr;    // [row_pad] shared lower bound on each query's k-th best score (key space)
+  // EPI_STORE
+  float* dbg_scores; // [rows][cols]
+  // EPI_MAXTOK
+  const float* bias;      // [rows] or null
+  const uint8_t* mask;    // [cols] 1 = valid token
+  float* out;             // [n_segs][rows]
+  int relu, log1p;
+};
+
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& m_tile, int& split) {
+  const int per_band = p.band_size * p.splits;
+  int b = u / per_band;
+  if (b > p.n_bands - 1) b = p.n_bands - 1;
+  const int rem = u - b * per_band;
+  const int mb = min(p.band_size, p.m_tiles - b * p.band_size);
+  split = rem / mb;
+  m_tile = b * p.band_size + rem % mb;
+}
+// columns [c0, c1) covered by a split; tiles start at c0 and step BN
+template <int EPI>
+__device__ __forceinline__ void split_cols(const GemmParams& p, int split, int64_t& c0, int64_t& c1) {
+  if (EPI == EPI_MAXTOK) {
+    const int64_t s0 = int64_t(split) * p.segs_per_split;
+    int64_t s1 = s0 + p.segs_per_split;
+    if (s1 > p.n_segs) s1 = p.n_segs;
+    c0 = s0 * p.seg_len;
+    c1 = s1 * p.seg_len;
+  } else {
+    const int64_t t0 = (int64_t(split) * p.n_tiles) / p.splits;
+    const int64_t t1 = (int64_t(split + 1) * p.n_tiles) / p.splits;
+    c0 = t0 * BN;
+    c1 = t1 * BN;
+    if (c1 > p.cols) c1 = p.cols;
+  }
+}
+
+// Cut a candidate list (n entries, ascending id order) back to its exact top-k, keeping id order.
+// Returns the score key of the k-th best entry.  All 32 lanes participate.
+static __device__ __noinline__ uint32_t warp_compact_topk(uint64_t* buf, int n, int k, uint32_t* hist, int lane) {
+  const uint32_t full = 0xFFFFFFFFu;
+  uint32_t prefix = 0;
+  uint32_t remaining = uint32_t(k);
+#pragma unroll 1
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = pass * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const uint32_t h = key_hi(ld_cg_u64(buf + i));
+      const bool match = (pass == 3) || ((h >> (shift + 8)) == prefix);
+      if (match) atomicAdd(&hist[(h >> shift) & 0xFFu], 1u);
+    }
+    __syncwarp();
+    const int base = 8 * (31 - lane);  // lane 0 owns the highest bins
+    uint32_t c[8];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c[i] = hist[base + 7 - i];
+      sum += c[i];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, incl, off);
+      if (lane >= off) incl += t;
+    }
+    const uint32_t excl = incl - sum;
+    const bool hit = (excl < remaining) && (remaining <= incl);
+    const uint32_t hm = __ballot_sync(full, hit);
+    const int src = hm ? (__ffs(hm) - 1) : 31;
+    uint32_t bin = 0, rem2 = 1;
+    if (lane == src) {
+      uint32_t acc = excl;
+      bool done = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!done && acc + c[i] >= remaining) {
+          bin = uint32_t(base + 7 - i);
+          rem2 = remaining - acc;
+          done = true;
+        }
+        if (!done) acc += c[i];
+      }
+    }
+    bin = __shfl_sync(full, bin, src);
+    rem2 = __shfl_sync(full, rem2, src);
+    prefix = (prefix << 8) | bin;
+    remaining = rem2;
+    __syncwarp();
+  }
+  const uint32_t vk = prefix;            // score key of the k-th best
+  const uint32_t keep_ties = remaining;  // how many entries equal to vk survive (lowest ids first)
+  // stable in-place compaction (write index never passes the read index)
+  uint32_t out = 0, ties_seen = 0;
+  const uint32_t lt = lanemask_lt();
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool in = i < n;
+    const uint64_t key = in ? ld_cg_u64(buf + i) : 0ull;
+    const uint32_t h = key_hi(key);
+    const bool gt = in && h > vk;
+    const bool eq = in && h == vk;
+    const uint32_t eqm = __ballot_sync(full, eq);
+    const uint32_t tie_rank = ties_seen + __popc(eqm & lt);
+    const bool keep = gt || (eq && tie_rank < keep_ties);
+    const uint32_t km = __ballot_sync(full, keep);
+    if (keep) st_cg_u64(buf + out + __popc(km & lt), key);
+    out += __popc(km);
+    ties_seen += __popc(eqm);
+  }
+  __syncwarp();
+  return vk;
+}
+
+constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier map (8 bytes each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then the TMEM pointer slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + SMEM_BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int m_tile, split;
+        int64_t c0, c1;
+        decode_unit(p, u, m_tile, split);
+        split_cols<EPI>(p, split, c0, c1);
+        for (int64_t cb = c0; cb < c1; cb += BN) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(a_dst, &tmA, kb * BK, m_tile * BM, full_bar(stage));
+            tma_load_2d(a_dst + A_BYTES, &tmB, kb * BK, int(cb), full_bar(stage));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int m_tile, split;
+        int64_t c0, c1;
+        decode_unit(p, u, m_tile, split);
+        split_cols<EPI>(p, split, c0, c1);
+        for (int64_t cb = c0; cb < c1; cb += BN) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+            const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+            const uint64_t b_desc = umma_desc_k_sw128(a_addr + A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc,
+                        (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          if (++acc == ACC_STAGES) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t* hist = hist_all + (warp - 2) * 256;
+    const uint32_t full = 0xFFFFFFFFu;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int m_tile, split;
+      int64_t c0, c1;
+      decode_unit(p, u, m_tile, split);
+      split_cols<EPI>(p, split, c0, c1);
+      const int64_t row = int64_t(m_tile) * BM + row_in_tile;
+      const bool row_valid = row < p.rows;
+      // EPI_TOPK per-row running state
+      uint64_t* buf = nullptr;
+      uint32_t cnt = 0;
+      float thr_local = -INFINITY;
+      float qs = 1.0f;
+      // EPI_MAXTOK per-row running state
+      float run_max = BF16_LOWEST;
+      float bias_v = 0.0f;
+      int64_t seg = 0, seg_end = 0;
+      if (EPI == EPI_TOPK) {
+        buf = p.cand + (int64_t(split) * p.row_pad + row) * p.cap;
+        if (row_valid && p.q_scale) qs = p.q_scale[row];
+      }
+      if (EPI == EPI_MAXTOK) {
+        if (row_valid && p.bias) bias_v = p.bias[row];
+        seg = c0 / p.seg_len;
+        seg_end = c0 + p.seg_len;
+      }
+      for (int64_t cb = c0; cb < c1; cb += BN) {
+        const int n_valid = (c1 - cb < int64_t(BN)) ? int(c1 - cb) : BN;
+        float thr = INFINITY;
+        if (EPI == EPI_TOPK && row_valid) {
+          const uint32_t g = ld_relaxed_u32(p.gthr + row);
+          const float tg = (g <= KEY_NEG_INF) ? -INFINITY : key_to_f32(g - 1u);  // s >= gthr  <=>  s > tg
+          thr = fmaxf(thr_local, tg);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 >= n_valid) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + uint32_t(c * 32), v);
+          tmem_ld_wait();
+          const int col_lim = n_valid - c * 32;  // columns >= col_lim are padding
+          if (EPI == EPI_STORE) {
+            if (row_valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < col_lim) p.dbg_scores[row * p.cols + cb + c * 32 + j] = __uint_as_float(v[j]);
+            }
+          } else if (EPI == EPI_TOPK) {
+            float cs_lane = 1.0f;
+            const bool has_cs = p.c_scale != nullptr;
+            if (has_cs) {
+              const int64_t dcol = cb + c * 32 + lane;
+              cs_lane = dcol < p.cols ? p.c_scale[dcol] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]) * qs;
+              if (has_cs) s *= __shfl_sync(full, cs_lane, j);
+              if (s > thr && j < col_lim) {
+                st_cg_u64(buf + cnt, make_key(f32_to_key(s), uint32_t(cb + c * 32 + j)));
+                ++cnt;
+              }
+            }
+            // keep >= 32 free slots for the next chunk; cut full lists back to their top-k
+            uint32_t need = __ballot_sync(full, cnt + 32u > uint32_t(p.cap));
+            while (need) {
+              const int r = __ffs(need) - 1;
+              need &= need - 1;
+              const int n_r = __shfl_sync(full, int(cnt), r);
+              const int64_t row_r = int64_t(m_tile) * BM + quarter * 32 + r;
+              uint64_t* buf_r = p.cand + (int64_t(split) * p.row_pad + row_r) * p.cap;
+              const uint32_t vk = warp_compact_topk(buf_r, n_r, p.k, hist, lane);
+              if (lane == r) {
+                cnt = uint32_t(p.k);
+                thr_local = key_to_f32(vk);
+                thr = fmaxf(thr, thr_local);
+                atomicMax(p.gthr + row, vk);  // publish: valid lower bound of this query's global k-th score
+              }
+            }
+          } else {  // EPI_MAXTOK
+            const int64_t tok = cb + c * 32 + lane;
+            const bool mval = (tok < c1) && (p.mask[tok] != 0);
+            const uint32_t mword = __ballot_sync(full, mval);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t n = cb + c * 32 + j;
+              if (j < col_lim) {
+                if (n == seg_end) {  // warp-uniform: a document ended right before this token
+                  float x = run_max;
+                  if (p.relu) x = fmaxf(x, 0.0f);
+                  if (p.log1p) x = log1pf(x);
+                  if (row_valid) p.out[seg * p.rows + row] = x;
+                  run_max = BF16_LOWEST;
+                  ++seg;
+                  seg_end += p.seg_len;
+                }
+                if ((mword >> j) & 1u) run_max = fmaxf(run_max, __uint_as_float(v[j]) + bias_v);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == ACC_STAGES) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      if (EPI == EPI_TOPK) p.counts[int64_t(split) * p.row_pad + row] = row_valid ? int32_t(cnt) : 0;
+      if (EPI == EPI_MAXTOK && c1 > c0) {
+        float x = run_max;
+        if (p.relu) x = fmaxf(x, 0.0f);
+        if (p.log1p) x = log1pf(x);
+        if (row_valid) p.out[seg * p.rows + row] = x;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host helpers
+inline PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols_used] with row pitch ld elements; box = [64 cols, box_rows], 128B swizzle.
+inline int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols_used, int64_t ld, int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return LR_ECUDA;
+  }
+  cuuint64_t gdim[2] = {cuuint64_t(cols_used), cuuint64_t(rows)};
+  cuuint64_t gstr[1] = {cuuint64_t(ld) * 2};
+  cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", int(r),
+              (long long)rows, (long long)cols_used, (long long)ld);
+    return LR_ECUDA;
+  }
+  return LR_OK;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+// balanced bands of row tiles: every band but the last holds band_size tiles
+inline void plan_bands(int m_tiles, int band_max, int& band_size, int& n_bands) {
+  if (band_max < 1) band_max = 1;
+  n_bands = (m_tiles + band_max - 1) / band_max;
+  if (n_bands < 1) n_bands = 1;
+  band_size = (m_tiles + n_bands - 1) / n_bands;
+  if (band_size < 1) band_size = 1;
+  n_bands = (m_tiles + band_size - 1) / band_size;
+}
+
+template <int EPI>
+inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
+                            cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GEMM_SMEM_TOTAL);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
+    return LR_ECUDA;
+  }
+  umma_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, st>>>(tmA, tmB, prm);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
+}
+
+}  // namespace lr

@@ -1,0 +1,153 @@
+"""Document sparse head (K3) — host side, seam S3.
+
+Mirrors
+  * ``get_sparse_attention_mask`` (reference finetune/sparse_pooling.py:23-59) — host logic on torch tensors;
+  * ``max_linear_mapping(input, weight[d,V], bias, attention_mask)`` (utils/max_linear_map.py:175-188) and
+    ``aggregate(hidden_states, lm_head, sparse_attention_mask)`` (finetune/sparse_pooling.py:244-278);
+  * ``HybridModel.get_sparse_emb`` relu / log1p / top-k (finetune/modeling_hybrid.py:183-201,
+    finetune/sparse_pooling.py:89-106);
+  * ``convert_sparse_reps_to_json`` (finetune/sparse_converter_mixin.py:25-60; rounding follows the in-repo
+    torch twin :103-160 — the Rust converter's rounding is not pinned by the reference).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _C
+from ._util import require_cuda, stream_ptr
+
+
+def get_prompt_mask(input_ids: torch.Tensor, sep_token_id: int) -> torch.Tensor:
+    """sparse_pooling.py:43-59."""
+    assert input_ids.ndim == 2
+    if not bool((input_ids == sep_token_id).any()):
+        return torch.zeros_like(input_ids, dtype=torch.bool)
+    positions = torch.argmax((input_ids == sep_token_id).int(), dim=-1)
+    if bool(torch.all(positions == input_ids.shape[-1] - 1)):
+        return torch.zeros_like(input_ids, dtype=torch.bool)
+    col = torch.arange(input_ids.shape[-1], device=input_ids.device).unsqueeze(0)
+    return col <= positions.unsqueeze(1)
+
+
+def get_sparse_attention_mask(input_ids: torch.Tensor, attention_mask: torch.Tensor, sep_token_id: int,
+                              remove_prompt: bool = False) -> torch.Tensor:
+    """Valid-token mask: attention mask minus position 0, minus the last valid position, minus the prompt
+    (sparse_pooling.py:23-41)."""
+    mask = attention_mask.bool().clone()
+    if remove_prompt:
+        mask = mask.masked_fill(get_prompt_mask(input_ids, sep_token_id), False)
+    bs = torch.arange(attention_mask.shape[0], device=attention_mask.device)
+    last = attention_mask.sum(dim=1) - 1
+    mask[bs, 0] = False
+    mask[bs, last] = False
+    return mask
+
+
+def max_linear_mapping(input: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                       attention_mask: Optional[torch.Tensor] = None, relu: bool = False, log1p: bool = False,
+                       weight_is_vd: bool = False) -> torch.Tensor:
+    """``max_t (input[b,t] @ weight + bias)`` over valid t -> [B, V] float32 (max_linear_map.py:175-188).
+
+    weight is [d, V] as in the reference (``lm_head.weight.T``); pass ``weight_is_vd=True`` to hand over
+    ``lm_head.weight`` ([V, d]) directly and skip the transpose copy.
+    """
+    h = require_cuda(input, "input")
+    if h.ndim != 3:
+        raise ValueError("input must be [B, S, d]")
+    B, S, d = h.shape
+    W = require_cuda(weight, "weight")
+    Wvd = W if weight_is_vd else W.t()
+    if Wvd.shape[1] != d:
+        raise ValueError("weight shape does not match the hidden size")
+    V = Wvd.shape[0]
+    h = h.to(torch.bfloat16).contiguous()
+    Wvd = Wvd.to(torch.bfloat16).contiguous()
+    if attention_mask is None:
+        mask = torch.ones((B, S), dtype=torch.uint8, device=h.device)
+    else:
+        mask = require_cuda(attention_mask, "attention_mask").to(torch.uint8).contiguous()
+        if mask.shape != (B, S):
+            raise ValueError("attention_mask must be [B, S]")
+    b = None if bias is None else require_cuda(bias, "bias").to(torch.float32).contiguous()
+    out = torch.empty((B, V), dtype=torch.float32, device=h.device)
+    lib = _C.load()
+    with torch.cuda.device(h.device):
+        _C.check(lib.lr_sparse_head_max(h.data_ptr(), Wvd.data_ptr(), None if b is None else b.data_ptr(),
+                                        mask.data_ptr(), B, S, d, V, int(relu), int(log1p), out.data_ptr(),
+                                        stream_ptr(h.device)))
+    return out
+
+
+def aggregate(hidden_states: torch.Tensor, lm_head, sparse_attention_mask: torch.Tensor,
+              sparse_use_max_aggregation: bool = True) -> torch.Tensor:
+    """sparse_pooling.py:244-278 for an ``nn.Linear``-like lm_head (``.weight`` [V, d], optional ``.bias``)."""
+    if not sparse_use_max_aggregation:
+        raise NotImplementedError("mean aggregation is the reference's memory-inefficient ablation; not on the hot path")
+    return max_linear_mapping(hidden_states, lm_head.weight, getattr(lm_head, "bias", None), sparse_attention_mask,
+                              weight_is_vd=True)
+
+
+def sparsify_quantize(reps: torch.Tensor, top_k: int = 0, min_tokens_to_keep: int = 8, quantization_factor: float = 100.0,
+                      cap: Optional[int] = None):
+    """top_k_sampling + clamp/round quantiser -> CSR (indptr int32 [B+1], token ids int32, impacts uint16)."""
+    x = require_cuda(reps, "reps").to(torch.float32).contiguous()
+    B, V = x.shape
+    dev = x.device
+    lib = _C.load()
+    if cap is None:
+        k_eff = max(top_k, min_tokens_to_keep) if top_k > 0 else V
+        cap = B * min(V, max(2 * k_eff, k_eff + 1024)) if top_k > 0 else B * V
+    indptr = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    tok = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    imp = torch.empty(max(cap, 1), dtype=torch.int16, device=dev)  # uint16 bit pattern
+    scratch = torch.empty(lib.lr_sparsify_scratch_bytes(B, V), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.lr_sparsify_quantize(x.data_ptr(), B, V, int(top_k), int(min_tokens_to_keep), float(quantization_factor),
+                                      indptr.data_ptr(), tok.data_ptr(), imp.data_ptr(), cap, scratch.data_ptr(),
+                                      stream_ptr(dev))
+    if rc == _C.LR_EWORKSPACE:  # ties at the threshold can exceed any a-priori bound: retry with the exact size
+        nnz = int(indptr[-1].item())
+        return sparsify_quantize(reps, top_k, min_tokens_to_keep, quantization_factor, cap=nnz)
+    _C.check(rc)
+    nnz = int(indptr[-1].item())
+    return indptr, tok[:nnz], imp[:nnz]
+
+
+def sparse_head(hidden_states: torch.Tensor, lm_head_weight: torch.Tensor, bias: Optional[torch.Tensor],
+                sparse_attention_mask: torch.Tensor, sparse_use_relu: bool = True,
+                sparse_use_log_saturation: bool = True, sparse_top_k: int = 0, sparse_min_tokens_to_keep: int = 8,
+                quantization_factor: float = 100.0):
+    """hidden [B,S,d] -> CSR of integer impacts: aggregate + get_sparse_emb + convert_sparse_reps_to_json in two
+    device passes (GEMM with max/relu/log1p epilogue, then select/quantise)."""
+    reps = max_linear_mapping(hidden_states, lm_head_weight, bias, sparse_attention_mask, relu=sparse_use_relu,
+                              log1p=sparse_use_log_saturation, weight_is_vd=True)
+    return sparsify_quantize(reps, sparse_top_k, sparse_min_tokens_to_keep, quantization_factor)
+
+
+def csr_to_json(indptr: torch.Tensor, tok: torch.Tensor, imp: torch.Tensor) -> list[dict[str, int]]:
+    """CSR -> the reference's ``list[dict[str(token_id) -> int]]``; an empty document becomes ``{"-1": 1}``
+    (sparse_converter_mixin.py:150-156)."""
+    ip = indptr.cpu().tolist()
+    t = tok.cpu().tolist()
+    v = (imp.cpu().to(torch.int32) & 0xFFFF).tolist()
+    out = []
+    for b in range(len(ip) - 1):
+        d = {str(t[i]): int(v[i]) for i in range(ip[b], ip[b + 1])}
+        out.append(d if d else {"-1": 1})
+    return out
+
+
+def convert_sparse_reps_to_json(reps: torch.Tensor, quantization_factor: int = 100,
+                                convert_id_to_token: bool = False, vocab_dict=None) -> list[dict[str, int]]:
+    """sparse_converter_mixin.py:25-60 on device (dense [B,V] in, list of dicts out)."""
+    if reps.ndim == 1:
+        reps = reps.unsqueeze(0)
+    indptr, tok, imp = sparsify_quantize(reps, top_k=0, quantization_factor=float(quantization_factor))
+    res = csr_to_json(indptr, tok, imp)
+    if convert_id_to_token:
+        if vocab_dict is None:
+            raise ValueError("vocab_dict is required when convert_id_to_token=True")
+        res = [{("[PAD]" if k == "-1" else vocab_dict[int(k)]): v for k, v in d.items()} for d in res]
+    return res

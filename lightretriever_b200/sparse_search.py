@@ -1,0 +1,229 @@
+"""Sparse impact search (K4) — host side, seam S4.
+
+Mirrors ``AnseriniSearch`` (reference retriever/anserini_search.py:31-216): ``index(corpus_emb, corpus_ids)`` takes the
+``list[dict[str(token_id) -> int impact]]`` produced by ``convert_sparse_reps_to_json`` (JsonVectorCollection) and may
+be called repeatedly (chunks are appended, anserini_search.py:89-111); ``retrieve_with_emb(query_emb, query_ids,
+top_k)`` takes the pseudo-query strings ``"id id id ..."`` emitted by ``EncodeCollator`` (inference/
+exact_search_base.py:393-435; a repeated id = a count) or ``{token_id: count}`` dicts; ``_clear()`` drops the index.
+Instead of JSONL on disk + a JVM, documents become a token-major inverted index in HBM and scoring is
+``lr_sparse_score_topk`` (csrc/sparse_score.cu).  Scores are the exact integer dot products Lucene's impact search
+computes (scripts/asymmetric_sparse_infer.ipynb:207-228); only matching documents are returned.
+"""
+from __future__ import annotations
+
+from collections import Counter
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _C
+from ._util import Workspace, require_cuda, stream_ptr
+
+_WS = Workspace()
+
+
+def json_to_csr(corpus_emb: Sequence[dict]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """list[dict[str|int -> int]] -> doc-major CSR. The reference's empty-document marker {"-1": 1} has no postings."""
+    indptr = np.zeros(len(corpus_emb) + 1, dtype=np.int64)
+    toks, imps = [], []
+    for i, d in enumerate(corpus_emb):
+        n = 0
+        for k, v in d.items():
+            t = int(k)
+            if t < 0 or int(v) <= 0:
+                continue
+            toks.append(t)
+            imps.append(int(v))
+            n += 1
+        indptr[i + 1] = indptr[i] + n
+    return indptr, np.asarray(toks, dtype=np.int32), np.asarray(imps, dtype=np.int64)
+
+
+def parse_queries(query_emb: Sequence, vocab_size: Optional[int] = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Pseudo-query strings / dicts -> CSR of (token, count). A token repeated in the string counts that many times,
+    which is what Lucene's boolean query of repeated terms scores (exact_search_base.py:413-424)."""
+    indptr = np.zeros(len(query_emb) + 1, dtype=np.int32)
+    toks, cnts = [], []
+    for i, qe in enumerate(query_emb):
+        if isinstance(qe, str):
+            c = Counter(int(t) for t in qe.split())
+        elif isinstance(qe, dict):
+            c = {int(k): int(v) for k, v in qe.items()}
+        else:
+            c = Counter(int(t) for t in qe)
+        n = 0
+        for t, v in c.items():
+            if t < 0 or v <= 0 or (vocab_size is not None and t >= vocab_size):
+                continue  # a token the corpus never produced matches nothing
+            toks.append(t)
+            cnts.append(v)
+            n += 1
+        indptr[i + 1] = indptr[i] + n
+    return indptr, np.asarray(toks, dtype=np.int32), np.asarray(cnts, dtype=np.int32)
+
+
+class ImpactIndex:
+    """Token-major inverted index resident in HBM: post_indptr [V+1] i64, post_doc i32 (ascending per token),
+    post_imp u16, plus per-token block pointers (see include/lr_b200.h)."""
+
+    def __init__(self, vocab_size: int, device: Optional[torch.device] = None, id_offset: int = 0):
+        self.V = int(vocab_size)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.id_offset = int(id_offset)
+        self._doc_chunks: list[tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = []
+        self.N = 0
+        self._built = None
+
+    def add_csr(self, indptr, tok, imp) -> None:
+        """Append documents given as doc-major CSR (numpy or torch, host or device)."""
+        ip = torch.as_tensor(indptr).to(torch.int64)
+        tk = torch.as_tensor(tok).to(self.device, torch.int64)
+        im = torch.as_tensor(imp).to(self.device)
+        if im.dtype == torch.int16:  # uint16 bit pattern from sparsify_quantize
+            im = im.to(torch.int32) & 0xFFFF
+        im = im.to(torch.int64)
+        if tk.numel() and (int(tk.min()) < 0 or int(tk.max()) >= self.V):
+            raise ValueError("token id out of range [0, vocab_size)")
+        if im.numel() and (int(im.min()) < 0 or int(im.max()) > 65535):
+            raise ValueError("impacts must fit uint16")
+        n_docs = ip.numel() - 1
+        lens = (ip[1:] - ip[:-1]).to(self.device)
+        doc = torch.repeat_interleave(torch.arange(self.N, self.N + n_docs, device=self.device), lens)
+        self._doc_chunks.append((doc, tk, im))
+        self.N += n_docs
+        self._built = None
+
+    def build(self):
+        if self._built is not None:
+            return self._built
+        if self.N == 0:
+            raise RuntimeError("index is empty")
+        doc = torch.cat([c[0] for c in self._doc_chunks])
+        tok = torch.cat([c[1] for c in self._doc_chunks])
+        imp = torch.cat([c[2] for c in self._doc_chunks])
+        # index-time (not the query path): stable sort by token keeps doc ids ascending inside a posting list
+        order = torch.argsort(tok, stable=True)
+        post_doc = doc[order].to(torch.int32).contiguous()
+        post_imp = imp[order].to(torch.int16).contiguous()  # uint16 bit pattern
+        counts = torch.bincount(tok, minlength=self.V)
+        post_indptr = torch.zeros(self.V + 1, dtype=torch.int64, device=self.device)
+        post_indptr[1:] = torch.cumsum(counts, 0)
+        lib = _C.load()
+        bd = lib.lr_sparse_block_docs()
+        nblk = (self.N + bd - 1) // bd
+        blockptr = torch.empty(self.V * (nblk + 1), dtype=torch.int32, device=self.device)
+        if post_doc.numel() == 0:
+            post_doc = torch.zeros(1, dtype=torch.int32, device=self.device)
+            post_imp = torch.zeros(1, dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            _C.check(lib.lr_sparse_build_blockptr(post_indptr.data_ptr(), post_doc.data_ptr(), self.V, self.N,
+                                                  blockptr.data_ptr(), stream_ptr(self.device)))
+        self._built = (post_indptr, post_doc, post_imp, blockptr)
+        return self._built
+
+    def search_device(self, q_indptr, q_tok, q_cnt, k: int, return_keys: bool = False):
+        post_indptr, post_doc, post_imp, blockptr = self.build()
+        dev = self.device
+        qi = torch.as_tensor(q_indptr).to(dev, torch.int32).contiguous()
+        qt = torch.as_tensor(q_tok).to(dev, torch.int32).contiguous()
+        qc = torch.as_tensor(q_cnt).to(dev, torch.int32).contiguous()
+        if qt.numel() == 0:
+            qt = torch.zeros(1, dtype=torch.int32, device=dev)
+            qc = torch.zeros(1, dtype=torch.int32, device=dev)
+        Q = qi.numel() - 1
+        lib = _C.load()
+        ws = _WS.get(lib.lr_sparse_score_workspace_bytes(Q, self.N, k), dev)
+        scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if return_keys else None
+        with torch.cuda.device(dev):
+            _C.check(lib.lr_sparse_score_topk(qi.data_ptr(), qt.data_ptr(), qc.data_ptr(), Q, post_indptr.data_ptr(),
+                                              post_doc.data_ptr(), post_imp.data_ptr(), blockptr.data_ptr(), self.V,
+                                              self.N, self.id_offset, int(k), scores.data_ptr(), ids.data_ptr(),
+                                              None if keys is None else keys.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              stream_ptr(dev)))
+        return (scores, ids, keys) if return_keys else (scores, ids)
+
+
+class ImpactSearch:
+    """``AnseriniSearch`` surface (anserini_search.py:31-216) over ``ImpactIndex`` (impact search only)."""
+
+    def __init__(self, model=None, batch_size: int = 128, corpus_chunk_size: Optional[int] = None,
+                 vocab_size: Optional[int] = None, **kwargs):
+        self.model = model
+        self.batch_size = batch_size
+        self.corpus_chunk_size = batch_size * 800 if corpus_chunk_size is None else corpus_chunk_size
+        self.show_progress_bar = kwargs.get("show_progress_bar", True)
+        self.convert_to_tensor = kwargs.get("convert_to_tensor", True)
+        if not kwargs.get("anserini_impact_search", True):
+            raise NotImplementedError("BM25 scoring is not on the hot path; only impact (dot-product) search is built")
+        self.vocab_size = vocab_size
+        self.device = kwargs.get("device", None)
+        self._index: Optional[ImpactIndex] = None
+        self._corpus_ids: list = []
+        self._pending: list = []
+        self.n_dumped = 0
+
+    @classmethod
+    def name(cls):
+        return "impact_b200_search"
+
+    def _clear(self):
+        self._index = None
+        self._corpus_ids = []
+        self._pending = []
+        self.n_dumped = 0
+
+    def encode(self, sentences, batch_size: int, **kwargs):
+        return self.model.encode(sentences=sentences, batch_size=batch_size, **kwargs)
+
+    def encode_queries(self, queries, batch_size: int, **kwargs):
+        return self.model.encode_queries(queries=queries, batch_size=batch_size, **kwargs)
+
+    def encode_corpus(self, corpus, batch_size: int, **kwargs):
+        return self.model.encode_corpus(corpus=corpus, batch_size=batch_size, **kwargs)
+
+    def index(self, corpus_emb, corpus_ids: Sequence[str]):
+        """corpus_emb: list[dict[str,int]] (JsonVectorCollection) or a CSR triple (indptr, tok, imp)."""
+        if isinstance(corpus_emb, tuple) and len(corpus_emb) == 3:
+            csr = corpus_emb
+        else:
+            if len(corpus_emb) and isinstance(corpus_emb[0], str):
+                corpus_emb = [dict(Counter(s.split())) for s in corpus_emb]  # JsonCollection pseudo-text
+            csr = json_to_csr(corpus_emb)
+        self._pending.append(csr)
+        self._corpus_ids.extend(corpus_ids)
+        self.n_dumped += len(corpus_ids)
+        self._index = None
+
+    def _ensure_index(self) -> ImpactIndex:
+        if self._index is None:
+            if not self._pending:
+                raise RuntimeError("index() must be called before retrieve_with_emb()")
+            V = self.vocab_size
+            if V is None:
+                V = 1 + max((int(torch.as_tensor(c[1]).max()) if len(c[1]) else 0) for c in self._pending)
+            idx = ImpactIndex(V, device=self.device)
+            for c in self._pending:
+                idx.add_csr(*c)
+            self._index = idx
+        return self._index
+
+    def retrieve_with_emb(self, query_emb: Sequence, query_ids: Sequence[str], top_k: int) -> dict:
+        idx = self._ensure_index()
+        qi, qt, qc = parse_queries(query_emb, idx.V)
+        k = min(int(top_k), 1024)
+        scores, ids = idx.search_device(qi, qt, qc, k)
+        scores = scores.cpu().numpy()
+        ids = ids.cpu().numpy()
+        results: dict[str, dict[str, float]] = {}
+        for i, qid in enumerate(query_ids):
+            row = {}
+            for doc, s in zip(ids[i].tolist(), scores[i].tolist()):
+                if doc < 0:
+                    continue
+                row[self._corpus_ids[doc]] = float(s)
+            if row:  # Lucene writes no TREC line for a query without hits (anserini_search.py:208-214)
+                results[qid] = row
+        return results
