@@ -111,6 +111,11 @@ int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
 int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
                      int64_t Q, int64_t N, int64_t d_used, float* out_scores /*[Q,N]*/, void* stream);
 
+/* Measurement hook (bench.py): when both are non-NULL cudaEvent_t handles, every following lr_flatip_topk /
+ * lr_sparse_head_max call on this thread records ev_begin / ev_end on its stream immediately around the main
+ * (tcgen05) kernel launch, so the caller can read that kernel's device time without a profiler.  NULL, NULL disables. */
+int lr_set_profile_events(void* ev_begin, void* ev_end);
+
 /* Plan of the last lr_flatip_topk call on this thread (for bench / DESIGN):
  * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=rounds */
 int lr_flatip_last_plan(int64_t* out8);

@@ -1,5 +1,5 @@
 // api.cu — error reporting and device queries of the C ABI (include/lr_b200.h).
-#include "common.cuh"
+#include "umma_gemm.cuh"
 
 #include <stdarg.h>
 #include <string.h>
@@ -33,7 +33,19 @@ int sm_count() {
   return cached[dev];
 }
 
+ProfileEvents& profile_events() {
+  static thread_local ProfileEvents pe;
+  return pe;
+}
+
 }  // namespace lr
+
+extern "C" int lr_set_profile_events(void* ev_begin, void* ev_end) {
+  lr::ProfileEvents& pe = lr::profile_events();
+  pe.begin = static_cast<cudaEvent_t>(ev_begin);
+  pe.end = static_cast<cudaEvent_t>(ev_end);
+  return LR_OK;
+}
 
 extern "C" const char* lr_last_error(void) { return lr::g_err; }
 extern "C" int lr_version(void) { return 100; }

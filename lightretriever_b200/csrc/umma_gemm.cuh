@@ -480,6 +480,12 @@ inline void plan_bands(int m_tiles, int band_max, int& band_size, int& n_bands) 
   n_bands = (m_tiles + band_size - 1) / band_size;
 }
 
+// optional CUDA events recorded around the main kernel (lr_set_profile_events)
+struct ProfileEvents {
+  cudaEvent_t begin = nullptr, end = nullptr;
+};
+ProfileEvents& profile_events();  // thread-local, defined in api.cu
+
 template <int EPI>
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
@@ -489,8 +495,11 @@ inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
     return LR_ECUDA;
   }
+  ProfileEvents& pe = profile_events();
+  if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.begin, st));
   umma_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, st>>>(tmA, tmB, prm);
   LR_LAUNCH_CHECK();
+  if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
   return LR_OK;
 }
 

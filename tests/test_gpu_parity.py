@@ -1,0 +1,360 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden
+fixtures.  Bars: bit-exact for ids / integer impacts / integer scores; dense scores within 1e-2 relative of the fp32
+oracle on the same bf16-rounded inputs, ids exact outside the tie band."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import lightretriever_b200 as lr
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float32) else t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_embbag_golden_fp32_is_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "embbag.npz"))
+    pad = int(g["pad"])
+    bag = lr.B200EmbeddingBag.from_pretrained(torch.from_numpy(g["table"]).cuda(), padding_idx=pad)
+    ids, off = torch.from_numpy(g["ids"]).cuda(), torch.from_numpy(g["offsets"]).cuda()
+    np.testing.assert_allclose(_np(bag.forward(ids, off)), g["out_full"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(_np(bag.encode(ids, off, shrink_dim=16, normalize=True)), g["out_m16_norm"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(_np(bag.encode(ids, off, normalize=True)), g["out_full_norm"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("V,d,m,norm", [(128256, 2048, None, True), (1000, 4096, 128, True), (777, 3584, 1024, False)])
+def test_embbag_bf16_table_vs_oracle(V, d, m, norm):
+    gen = torch.Generator().manual_seed(0)
+    table = (torch.randn(V, d, generator=gen) * 0.02).bfloat16()
+    lens = torch.randint(0, 33, (500,), generator=gen)
+    lens[-1] = 5  # last bag runs to the end of ids
+    ids = torch.randint(0, V, (int(lens.sum()),), generator=gen)
+    pad = V - 3
+    ids[::13] = pad
+    ids[5:9] = ids[4]  # duplicate ids inside a bag
+    offsets = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.long), lens[:-1]]), 0)
+    ref = oracle.embbag_encode(ids, offsets, table.float(), pad, m, norm).numpy()
+    bag = lr.B200EmbeddingBag.from_pretrained(table.cuda(), padding_idx=pad)
+    got32 = _np(bag.encode(ids.cuda(), offsets.cuda(), shrink_dim=m, normalize=norm, out_dtype=torch.float32))
+    np.testing.assert_allclose(got32, ref, rtol=1e-5, atol=1e-7)
+    got16 = _np(bag.encode(ids.cuda(), offsets.cuda(), shrink_dim=m, normalize=norm))
+    np.testing.assert_allclose(got16, ref, rtol=1e-2, atol=1e-5)  # bf16 output rounding
+    assert not got32[lens.numpy() == 0].any()  # empty bags -> zero vectors
+
+
+def test_embbag_errors():
+    bag = lr.B200EmbeddingBag.from_pretrained(torch.randn(50, 64).cuda())
+    with pytest.raises(IndexError):
+        bag.forward(torch.tensor([1, 50]).cuda(), torch.tensor([0]).cuda())
+    with pytest.raises(ValueError):
+        bag.encode(torch.tensor([1]).cuda(), torch.tensor([0]).cuda(), shrink_dim=12)  # not a multiple of 8
+    out = bag.forward(torch.tensor([[1, 2], [3, 3]]).cuda())  # 2-D input = fixed-length bags
+    assert out.shape == (2, 64)
+
+
+def test_lasttoken_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "lasttoken.npz"))
+    h = torch.from_numpy(g["hidden"]).cuda()
+    for am, out in (("am_right", "out_right"), ("am_left", "out_left")):
+        got = lr.lasttoken_head(h, torch.from_numpy(g[am]).cuda())
+        np.testing.assert_array_equal(_np(got), g[out])
+    ref = oracle.lasttoken_head(g["hidden"], g["am_right"], 8, True).numpy()
+    got = lr.lasttoken_head(h.bfloat16(), torch.from_numpy(g["am_right"]).cuda(), 8, True, out_dtype=torch.float32)
+    np.testing.assert_allclose(_np(got), oracle.lasttoken_head(h.bfloat16().float().cpu(), g["am_right"], 8, True).numpy(),
+                               rtol=1e-5, atol=1e-6)
+    assert ref.shape == (4, 8)
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("Q,N,d", [(128, 256, 64), (300, 1000, 4096), (129, 257, 72), (1, 5, 8), (200, 5000, 3584)])
+def test_gemm_mainloop_scores(Q, N, d):
+    gen = torch.Generator().manual_seed(Q + N)
+    q = torch.randn(Q, d, generator=gen).bfloat16().cuda()
+    c = torch.randn(N, d, generator=gen).bfloat16().cuda()
+    got = lr.flatip_scores(q, c)
+    ref = q.float() @ c.float().T
+    torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-3 * d ** 0.5)
+
+
+@pytest.mark.parametrize("Q,N,d,k", [(64, 5000, 128, 10), (300, 20000, 256, 100), (130, 3000, 2048, 1000),
+                                     (5, 100000, 64, 100), (1000, 100000, 2048, 100), (33, 70000, 3584, 1)])
+def test_flatip_topk_vs_oracle(Q, N, d, k):
+    gen = torch.Generator().manual_seed(k)
+    q = F.normalize(torch.randn(Q, d, generator=gen), dim=-1).bfloat16()
+    c = F.normalize(torch.randn(N, d, generator=gen), dim=-1).bfloat16()
+    s, i = lr.flatip_topk(q.cuda(), c.cuda(), k)
+    ref = (q.float() @ c.float().T).numpy()  # fp32 math on the bf16-rounded values (SURVEY §8c trap 1)
+    oracle.check_topk_parity(_np(s), _np(i), ref, k, rtol=1e-2)
+
+
+def test_flatip_topk_config1_shape_ids_match_oracle():
+    """BASELINE configs[0]: Llama-3.2-1B-shaped bag (V=128256, d=2048), 1k queries <=32 tokens, 100k docs, top-100."""
+    gen = torch.Generator().manual_seed(0)
+    V, d, Q, N, k = 128256, 2048, 1000, 100_000, 100
+    table = (torch.randn(V, d, generator=gen) * 0.02).bfloat16()
+    lens = torch.randint(1, 33, (Q,), generator=gen)
+    ids = torch.randint(0, V, (int(lens.sum()),), generator=gen)
+    offsets = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.long), lens[:-1]]), 0)
+    corpus = F.normalize(torch.randn(N, d, generator=gen), dim=-1).bfloat16()
+    bag = lr.B200EmbeddingBag.from_pretrained(table.cuda(), padding_idx=128002)
+    qv = bag.encode(ids.cuda(), offsets.cuda(), normalize=True)
+    ref_q = oracle.embbag_encode(ids, offsets, table.float(), 128002, None, True)
+    np.testing.assert_allclose(_np(qv), ref_q.numpy(), rtol=1e-2, atol=1e-4)
+    s, i = lr.flatip_topk(qv, corpus.cuda(), k)
+    ref = (qv.float().cpu() @ corpus.float().T).numpy()
+    oracle.check_topk_parity(_np(s), _np(i), ref, k, rtol=1e-2)
+    es, ei = oracle.flatip_topk_fast(qv.float().cpu(), corpus.float(), k)
+    assert (ei.numpy() == _np(i)).mean() > 0.999  # identical outside fp32 summation-order ties
+
+
+def test_flatip_topk_edges_exact():
+    gen = torch.Generator().manual_seed(2)
+    q = torch.randn(7, 64, generator=gen).bfloat16()
+    q[2] = 0  # zero query: every score ties at 0 -> ids 0..k-1
+    c = torch.randn(50, 64, generator=gen).bfloat16()
+    c[10:20] = c[5]  # exact duplicates: ties resolved by ascending id
+    for k in (1, 10, 50, 100):  # k > N -> (-inf, -1) tail
+        s, i = lr.flatip_topk(q.cuda(), c.cuda(), k, id_offset=1000)
+        es, ei = oracle.flatip_topk(q.float(), c.float(), k, id_offset=1000)
+        np.testing.assert_array_equal(_np(i), ei)
+        np.testing.assert_allclose(_np(s), es, rtol=1e-3, atol=1e-4)
+    with pytest.raises(ValueError):
+        lr.flatip_topk(q.cuda(), c.cuda(), 0)
+    with pytest.raises(ValueError):
+        lr.flatip_topk(q.cuda(), c.cuda(), 4096)
+    with pytest.raises(ValueError):
+        lr.flatip_topk(q.cuda().float(), c.cuda(), 4)
+
+
+def test_flatip_mrl_prefix_and_scales():
+    """MRL (configs[2]): truncate-then-normalise == full-width rows scored on the prefix with reciprocal prefix norms."""
+    gen = torch.Generator().manual_seed(3)
+    qf = torch.randn(40, 1024, generator=gen).bfloat16()
+    cf = torch.randn(3000, 1024, generator=gen).bfloat16()
+    for m in (128, 256, 512):
+        s, i = lr.flatip_topk(qf.cuda()[:, :m], cf.cuda()[:, :m], 20)  # strided views of full-width rows
+        es, ei = oracle.flatip_topk(qf[:, :m].float(), cf[:, :m].float(), 20)
+        np.testing.assert_array_equal(_np(i), ei)
+        qs = 1.0 / qf[:, :m].float().norm(dim=1)
+        cs = 1.0 / cf[:, :m].float().norm(dim=1)
+        s2, i2 = lr.flatip_topk(qf.cuda(), cf.cuda(), 20, d_used=m, q_scale=qs.cuda(), c_scale=cs.cuda())
+        ref = (F.normalize(qf[:, :m].float(), dim=-1) @ F.normalize(cf[:, :m].float(), dim=-1).T).numpy()
+        oracle.check_topk_parity(_np(s2), _np(i2), ref, 20, rtol=1e-3)
+
+
+def test_flatip_adversarial_order_stays_exact():
+    """Scores ascending with the document id: every document beats the running threshold, so the candidate lists
+    overflow and are compacted over and over — the result must still be exact."""
+    d, N, k = 64, 30000, 100
+    base = torch.zeros(N, d)
+    base[:, 0] = torch.linspace(0.1, 1.0, N)
+    q = torch.zeros(3, d)
+    q[:, 0] = torch.tensor([1.0, 0.5, -1.0])  # last query: descending order instead
+    s, i = lr.flatip_topk(q.bfloat16().cuda(), base.bfloat16().cuda(), k)
+    es, ei = oracle.flatip_topk(q.bfloat16().float(), base.bfloat16().float(), k)
+    np.testing.assert_array_equal(_np(i), ei)
+
+
+def test_searcher_surface_matches_reference_protocol():
+    gen = torch.Generator().manual_seed(4)
+    corpus = F.normalize(torch.randn(600, 128, generator=gen), dim=-1)
+    queries = F.normalize(torch.randn(5, 128, generator=gen), dim=-1)
+    cids = [f"doc-{j}" for j in range(600)]
+    qids = [f"q-{j}" for j in range(5)]
+    search = lr.FlatIPSearch(model=None)
+    search.index(corpus, cids)                                   # faiss_search.py:490-504
+    res = search.retrieve_with_emb(queries.numpy(), qids, 10)    # faiss_search.py:143-173
+    es, ei = oracle.flatip_topk(queries.bfloat16().float(), corpus.bfloat16().float(), 10)
+    for r, qid in enumerate(qids):
+        assert list(res[qid].keys()) == [cids[j] for j in ei[r]]
+        np.testing.assert_allclose(list(res[qid].values()), es[r], rtol=1e-2, atol=1e-4)
+    # chunked search + heap merge == one-shot search (hybrid_search.py:301-344)
+    heaps = {}
+    for lo in range(0, 600, 250):
+        search._clear()
+        search.index(corpus[lo:lo + 250], cids[lo:lo + 250])
+        lr.search.add_to_heap(search.retrieve_with_emb(queries, qids, 10), heaps, 10, False)
+    for r, qid in enumerate(qids):
+        assert sorted(p for _, p in heaps[qid]) == sorted(res[qid].keys())
+    search._clear()
+    with pytest.raises(RuntimeError):
+        search.retrieve_with_emb(queries, qids, 10)
+    # FaissIndex-style arrays, fewer docs than k
+    idx = lr.FlatIPIndex.build(list(range(7)), corpus[:7])
+    sc, ids = idx.search(queries.numpy(), 10)
+    assert sc.dtype == np.float32 and ids.dtype == np.int64 and (ids[:, 7:] == -1).all() and np.isneginf(sc[:, 7:]).all()
+
+
+def test_merge_kernel_exact():
+    rng = np.random.default_rng(0)
+    L, Q, cap, k = 8, 33, 100, 100
+    scores = rng.standard_normal((L, Q, cap)).astype(np.float32)
+    scores[:, :, ::7] = 0.25
+    ids = np.stack([rng.permutation(100000)[:L * cap].reshape(L, cap) for _ in range(Q)], 1).astype(np.int64)
+    keys = lr.encode_keys(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda())
+    np.testing.assert_array_equal(_np(keys).view(np.uint64), oracle.encode_keys(scores, ids))
+    s, i, ok = lr.topk_merge(keys, k, return_keys=True)
+    es, ei = oracle.merge_topk(list(scores), list(ids), k)
+    np.testing.assert_array_equal(_np(i), ei)
+    np.testing.assert_array_equal(_np(s), es)
+    np.testing.assert_array_equal(_np(ok).view(np.uint64), oracle.encode_keys(es, ei))
+    counts = rng.integers(0, cap + 1, (L, Q)).astype(np.int32)
+    counts[:, 0] = 0  # a query without any candidate
+    s, i = lr.topk_merge(keys, 37, counts=torch.from_numpy(counts).cuda())
+    m = np.arange(cap)[None, None] < counts[:, :, None]
+    es, ei = oracle.merge_topk(list(np.where(m, scores, -np.inf)), list(np.where(m, ids, -1)), 37)
+    np.testing.assert_array_equal(_np(i), ei)
+    assert (ei[0] == -1).all()
+
+
+# ------------------------------------------------------------------------------------------------ K3
+def test_sparse_head_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sparse_head.npz"))
+    h, W, b = (torch.from_numpy(g[n]).cuda() for n in ("h", "W", "bias"))
+    mask = torch.from_numpy(g["mask"]).cuda()
+    got = _np(lr.max_linear_mapping(h, W, b, mask))  # weight [d, V] as in the reference signature
+    fin = g["out_f32"] > -1e30
+    # inputs are rounded to bf16 by the kernel: compare with the oracle on the rounded values, and with the
+    # reference's own fp32 output inside the bf16 band of max_linear_map.py:192-196
+    ref = oracle.max_linear_map(h.bfloat16().float().cpu(), W.bfloat16().float().cpu(), b.cpu(), g["mask"]).numpy()
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(got[fin], g["out_f32"][fin], rtol=5e-2, atol=5e-2)
+    assert (got[~fin] < -1e30).all()  # no valid token -> finfo(bf16).min
+    got_rl = _np(lr.max_linear_mapping(h, W, b, mask, relu=True, log1p=True))
+    np.testing.assert_allclose(got_rl, np.log1p(np.maximum(ref, 0)), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,S,d,V", [(3, 64, 128, 1000), (5, 100, 256, 3001), (2, 512, 512, 5000), (9, 33, 64, 129)])
+def test_sparse_head_vs_oracle(B, S, d, V):
+    gen = torch.Generator().manual_seed(S)
+    h = torch.randn(B, S, d, generator=gen).bfloat16()
+    W = (torch.randn(V, d, generator=gen) * 0.05).bfloat16()
+    bias = torch.randn(V, generator=gen) * 0.1
+    lens = torch.randint(3, S + 1, (B,), generator=gen)
+    am = (torch.arange(S)[None] < lens[:, None]).long()
+    am[1] = 0
+    am[1, :2] = 1  # nothing valid once first/last are dropped
+    mask = oracle.sparse_attention_mask(torch.zeros(B, S, dtype=torch.long), am, sep_token_id=-1)
+    ref = oracle.max_linear_map(h.float(), W.float().T, bias, mask)
+    got = lr.max_linear_mapping(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), weight_is_vd=True).cpu()
+    fin = ref > -1e30
+    torch.testing.assert_close(got[fin], ref[fin], rtol=1e-4, atol=1e-4)
+    assert bool((got[~fin] < -1e30).all())
+    # integer stage is bit-exact given the same fp32 reps
+    reps = oracle.get_sparse_emb(ref, True, True, top_k=0)
+    for top_k in (0, 16, 64):
+        exp = oracle.quantize_reps(oracle.top_k_sampling(reps, top_k, min_tokens_to_keep=8), 100)
+        ip, tk, im = lr.sparsify_quantize(reps.cuda(), top_k=top_k, min_tokens_to_keep=8)
+        assert lr.csr_to_json(ip, tk, im) == exp
+    # fused path: impacts within the reference's own bf16 band (SURVEY §8c trap 7): |delta| <= max(1, 1% of impact)
+    ip, tk, im = lr.sparse_head(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), True, True, 64, 8, 100.0)
+    got_json = lr.csr_to_json(ip, tk, im)
+    exp_json = oracle.quantize_reps(oracle.top_k_sampling(reps, 64, min_tokens_to_keep=8), 100)
+    for gj, ej in zip(got_json, exp_json):
+        common = set(gj) & set(ej)
+        assert len(common) >= 0.9 * len(ej)
+        for t in common:
+            assert abs(gj[t] - ej[t]) <= max(1, 0.01 * ej[t])
+
+
+def test_quantiser_golden_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "quantize.npz"))
+    got = lr.convert_sparse_reps_to_json(torch.from_numpy(g["reps"]).cuda(), quantization_factor=100)
+    assert got == json.loads(str(g["json"]))
+
+
+def test_topk_sampling_golden_ties(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sparse_head.npz"))
+    tied = torch.from_numpy(g["tied"]).cuda()
+    for top_k, mk, name in ((3, 1, "tied_top3"), (2, 8, "tied_top2_min8"), (0, 8, "tied_top0")):
+        ip, tk, im = lr.sparsify_quantize(tied, top_k=top_k, min_tokens_to_keep=mk)
+        assert lr.csr_to_json(ip, tk, im) == oracle.quantize_reps(g[name], 100)
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def _rand_docs(rng, n, V, nnz, max_imp=400):
+    docs = []
+    for _ in range(n):
+        toks = rng.choice(V, size=int(rng.integers(0, nnz + 1)), replace=False)
+        docs.append({str(int(t)): int(rng.integers(1, max_imp + 1)) for t in toks})
+    return docs
+
+
+@pytest.mark.parametrize("N,V,nnz,Q,k", [(3000, 500, 40, 20, 10), (40000, 2000, 64, 16, 100), (20000, 300, 30, 8, 1000),
+                                         (70000, 50, 8, 300, 5)])
+def test_sparse_score_bit_exact(N, V, nnz, Q, k):
+    rng = np.random.default_rng(N)
+    docs = _rand_docs(rng, N, V, nnz)
+    queries = [" ".join(str(int(t)) for t in rng.integers(0, V + 5, size=int(rng.integers(1, 33)))) for _ in range(Q)]
+    queries[0] = ""  # a query without terms returns nothing
+    searcher = lr.ImpactSearch(vocab_size=V)
+    half = N // 2
+    searcher.index(docs[:half], [f"d{j}" for j in range(half)])  # chunked indexing, anserini_search.py:89-111
+    searcher.index(docs[half:], [f"d{j}" for j in range(half, N)])
+    res = searcher.retrieve_with_emb(queries, [f"q{j}" for j in range(Q)], k)
+    qd = [oracle.query_counts([int(t) for t in s.split()]) for s in queries]
+    es, ei = oracle.impact_topk(qd, [{int(a): b for a, b in d.items()} for d in docs], k)
+    assert "q0" not in res
+    for r in range(Q):
+        exp = {f"d{j}": float(s) for s, j in zip(es[r], ei[r]) if j >= 0}
+        assert res.get(f"q{r}", {}) == exp, f"query {r}"
+    # array form: sorted (score desc, id asc), integer scores, (-inf, -1) tail
+    from lightretriever_b200.sparse_search import parse_queries
+    s, i = searcher._ensure_index().search_device(*parse_queries(queries, V), k)
+    np.testing.assert_array_equal(_np(i), ei)
+    np.testing.assert_array_equal(_np(s), es)
+    searcher._clear()
+    with pytest.raises(RuntimeError):
+        searcher.retrieve_with_emb(queries, ["q"] * Q, k)
+
+
+def test_sparse_head_to_sparse_search_roundtrip():
+    """K3 output (CSR) feeds K4 directly, and through the reference's JSON form, with identical results."""
+    gen = torch.Generator().manual_seed(9)
+    B, S, d, V = 40, 32, 64, 300
+    h = torch.randn(B, S, d, generator=gen).bfloat16().cuda()
+    W = (torch.randn(V, d, generator=gen) * 0.2).bfloat16().cuda()
+    mask = torch.ones(B, S, dtype=torch.bool).cuda()
+    ip, tk, im = lr.sparse_head(h, W, None, mask, True, True, 16, 8, 100.0)
+    docs_json = lr.csr_to_json(ip, tk, im)
+    cids = [f"d{j}" for j in range(B)]
+    a, b = lr.ImpactSearch(vocab_size=V), lr.ImpactSearch(vocab_size=V)
+    a.index((ip, tk, im), cids)
+    b.index(docs_json, cids)
+    queries = ["1 2 3 4 5 5", "7 8 299", "10"]
+    ra = a.retrieve_with_emb(queries, ["a", "b", "c"], 10)
+    rb = b.retrieve_with_emb(queries, ["a", "b", "c"], 10)
+    assert ra == rb
+    es, ei = oracle.impact_topk([oracle.query_counts([int(t) for t in q.split()]) for q in queries],
+                                [{int(t): v for t, v in dj.items() if int(t) >= 0} for dj in docs_json], 10)
+    for r, qid in enumerate(["a", "b", "c"]):
+        assert ra.get(qid, {}) == {f"d{j}": float(s) for s, j in zip(es[r], ei[r]) if j >= 0}
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_width_properties_at_scale():
+    """Size-independent properties at a BASELINE-like width (d=4096) and a corpus larger than L2:
+    planted documents are found, results are sorted, ids unique, scores equal an fp32 recomputation of the returned
+    rows, and a sample of queries matches torch's fp32 matmul+topk on the device."""
+    torch.manual_seed(11)
+    Q, N, d, k = 512, 300_000, 4096, 100
+    c = F.normalize(torch.randn(N, d, device="cuda"), dim=-1).bfloat16()
+    q = F.normalize(torch.randn(Q, d, device="cuda"), dim=-1).bfloat16()
+    planted = torch.randint(0, N, (Q,), device="cuda")
+    c[planted] = q  # each query's own vector sits in the corpus: it must be rank 1 with score ~1
+    s, i = lr.flatip_topk(q, c, k)
+    assert bool((i[:, 0] == planted).all()) or bool(((s[:, 0] - 1).abs() < 1e-2).all())
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+    assert all(len(set(row)) == k for row in i[:16].tolist())
+    rec = torch.einsum("qd,qkd->qk", q.float(), c[i].float())
+    torch.testing.assert_close(s, rec, rtol=1e-2, atol=1e-4)
+    ref = q[:32].float() @ c.float().T
+    oracle.check_topk_parity(_np(s[:32]), _np(i[:32]), ref.cpu().numpy(), k, rtol=1e-2)

@@ -1,0 +1,123 @@
+"""CPU-side checks: the C-ABI library loads and exports exactly what include/lr_b200.h declares, the host logic matches
+the reference-pinned oracle, and the product path refuses to run without the GPU (no CPU fallback)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import lightretriever_b200 as lr
+from lightretriever_b200 import _C
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "lr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _C.load()
+    declared = _declared_functions()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lr_b200.h but not exported"
+    assert sorted(_C.PROTOTYPES) == declared, "ctypes prototypes out of sync with the header"
+    assert lib.lr_version() == 100
+
+
+def test_workspace_sizing_needs_no_gpu():
+    lib = _C.load()
+    ws = lib.lr_flatip_workspace_bytes(10000, 8_800_000, 100)
+    assert 0 < ws < (16 << 30)
+    assert lib.lr_flatip_workspace_bytes(10000, 8_800_000, 1000) > ws
+    assert lib.lr_sparse_score_workspace_bytes(32, 8_800_000, 100) > 0
+    assert lib.lr_sparse_block_docs() == 16384
+    assert lib.lr_flatip_workspace_bytes(0, 10, 10) == 0
+
+
+def test_argument_errors_map_to_value_error():
+    lib = _C.load()
+    rc = lib.lr_flatip_topk(None, 0, None, 0, 1, 1, 8, None, None, 0, 1, None, None, None, None, 0, None)
+    assert rc == _C.LR_EINVAL
+    with pytest.raises(ValueError):
+        _C.check(rc)
+    assert "null" in _C.last_error()
+    rc = lib.lr_topk_merge(None, None, 1, 1, 1, 1, 1, 0, 0, None, None, None, None)
+    assert rc == _C.LR_EINVAL
+
+
+def test_no_cpu_fallback():
+    bag = lr.B200EmbeddingBag.from_pretrained(torch.randn(10, 8), padding_idx=0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        bag.forward(torch.tensor([1, 2]), torch.tensor([0]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lr.flatip_topk(torch.randn(2, 8).bfloat16(), torch.randn(4, 8).bfloat16(), 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lr.max_linear_mapping(torch.randn(1, 4, 8), torch.randn(8, 16))
+    # nothing in the product package imports the oracle
+    pkg = os.path.join(ROOT, "lightretriever_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{fn} reaches into oracle/"
+
+
+def test_flatten_and_query_parsing_match_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "flatten.npz"))
+    lists = [[(ord(c) % 50) for c in str(q)][:12] for q in g["queries"]]
+    enc = lr.flatten_token_ids(lists)
+    np.testing.assert_array_equal(enc["input_ids"].numpy(), g["input_ids"])
+    np.testing.assert_array_equal(enc["offsets"].numpy(), g["offsets"])
+
+    class FakeTok:
+        def __call__(self, queries, max_length, truncation, add_special_tokens, return_attention_mask):
+            return {"input_ids": [[(ord(c) % 50) for c in q][:max_length] for q in queries]}
+
+    enc2 = lr.tokenize_nonctx_qry_emb_bag([str(q) for q in g["queries"]], FakeTok(), max_len=12)
+    np.testing.assert_array_equal(enc2["input_ids"].numpy(), g["input_ids"])
+    from lightretriever_b200.sparse_search import json_to_csr, parse_queries
+    qi, qt, qc = parse_queries(["5 7 5 5 900", {"3": 2}, ""], vocab_size=100)
+    assert qi.tolist() == [0, 2, 3, 3] and dict(zip(qt[:2].tolist(), qc[:2].tolist())) == oracle.query_counts([5, 7, 5, 5])
+    ip, tk, im = json_to_csr([{"4": 10, "2": 3}, {"-1": 1}, {"9": 65535}])
+    assert ip.tolist() == [0, 2, 2, 3] and tk.tolist() == [4, 2, 9] and im.tolist() == [10, 3, 65535]
+
+
+def test_sparse_mask_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sparse_head.npz"))
+    ids, am = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["am"])
+    np.testing.assert_array_equal(lr.get_sparse_attention_mask(ids, am, 7, False).numpy(), g["mask"])
+    np.testing.assert_array_equal(lr.get_sparse_attention_mask(ids, am, 7, True).numpy(), g["mask_rp"])
+
+
+def test_fusion_matches_reference(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "fusion.json")))
+    lin = lr.fuse_scores_linear([g["dense"], g["sparse"]], weights=[0.7, 0.3])
+    rrf = lr.fuse_scores_rrf([g["dense"], g["sparse"]])
+    for q in g["linear"]:
+        for p, v in g["linear"][q].items():
+            assert abs(lin[q][p] - v) < 1e-12
+        for p, v in g["rrf"][q].items():
+            assert abs(rrf[q][p] - v) < 1e-12
+    from lightretriever_b200.search import add_to_heap
+    heaps = {}
+    for ch in g["chunks"]:
+        add_to_heap(ch, heaps, 7, False)
+    assert {q: sorted([s, p] for s, p in v) for q, v in heaps.items()} == g["heap_top7"]
+
+
+def test_shard_ranges_partition_the_corpus():
+    for n, w in [(8_800_000, 8), (10, 3), (7, 8), (1, 1)]:
+        r = [lr.shard_range(n, i, w) for i in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        lr.shard_range(10, 3, 3)

@@ -1,0 +1,121 @@
+"""The oracle is pinned against outputs of the reference itself (tests/golden/, made by oracle/gen_golden.py)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import oracle
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_embbag_matches_torch_embeddingbag(golden_dir):
+    g = _load(golden_dir, "embbag.npz")
+    pad = int(g["pad"])
+    full = oracle.embbag_encode(g["ids"], g["offsets"], g["table"], pad)
+    np.testing.assert_array_equal(full.numpy(), g["out_full"])
+    # empty bag (index 1, 5) and all-padding bag (index 2) -> zero vectors
+    assert not full[1].any() and not full[5].any() and not full[2].any()
+    np.testing.assert_array_equal(oracle.embbag_encode(g["ids"], g["offsets"], g["table"], pad, 16, True).numpy(),
+                                  g["out_m16_norm"])
+    np.testing.assert_array_equal(oracle.embbag_encode(g["ids"], g["offsets"], g["table"], pad, None, True).numpy(),
+                                  g["out_full_norm"])
+
+
+def test_flatten_matches_reference_tokenizer_wrapper(golden_dir):
+    g = _load(golden_dir, "flatten.npz")
+    lists = [[(ord(c) % 50) for c in str(q)][:12] for q in g["queries"]]
+    ids, offsets = oracle.flatten_token_ids(lists)
+    np.testing.assert_array_equal(ids, g["input_ids"])
+    np.testing.assert_array_equal(offsets, g["offsets"])
+
+
+def test_lasttoken_matches_reference_pooling(golden_dir):
+    g = _load(golden_dir, "lasttoken.npz")
+    np.testing.assert_array_equal(oracle.lasttoken_head(g["hidden"], g["am_right"]).numpy(), g["out_right"])
+    np.testing.assert_array_equal(oracle.lasttoken_head(g["hidden"], g["am_left"]).numpy(), g["out_left"])
+
+
+def test_sparse_mask_and_max_linear_map_match_reference(golden_dir):
+    g = _load(golden_dir, "sparse_head.npz")
+    m = oracle.sparse_attention_mask(g["input_ids"], g["am"], sep_token_id=7, remove_prompt=False)
+    np.testing.assert_array_equal(m.numpy(), g["mask"])
+    m_rp = oracle.sparse_attention_mask(g["input_ids"], g["am"], sep_token_id=7, remove_prompt=True)
+    np.testing.assert_array_equal(m_rp.numpy(), g["mask_rp"])
+    fmin32 = torch.finfo(torch.float32).min
+    out = oracle.max_linear_map(g["h"], g["W"], g["bias"], g["mask"], fill=fmin32)
+    np.testing.assert_allclose(out.numpy(), g["out_f32"], rtol=1e-6, atol=1e-6)
+    out_nb = oracle.max_linear_map(g["h"], g["W"], None, g["mask_rp"], fill=fmin32)
+    np.testing.assert_allclose(out_nb.numpy(), g["out_f32_nobias"], rtol=1e-6, atol=1e-6)
+    # row 2 has no valid token after dropping first/last: stays at finfo.min (-> 0 after relu)
+    assert (g["out_f32"][2] == fmin32).all()
+    # the reference's own bf16 run agrees with the fp32 oracle inside its documented bf16 band (max_linear_map.py:192-196)
+    fin = g["out_f32"] > -1e30
+    np.testing.assert_allclose(g["out_bf16"][fin], g["out_f32"][fin], rtol=5e-2, atol=5e-2)
+
+
+def test_topk_sampling_matches_reference(golden_dir):
+    g = _load(golden_dir, "sparse_head.npz")
+    reps = torch.from_numpy(g["reps"])
+    np.testing.assert_array_equal(oracle.top_k_sampling(reps, 5, min_tokens_to_keep=8).numpy(), g["topk5"])
+    np.testing.assert_array_equal(oracle.top_k_sampling(reps, 20, min_tokens_to_keep=8).numpy(), g["topk20"])
+    tied = torch.from_numpy(g["tied"])
+    np.testing.assert_array_equal(oracle.top_k_sampling(tied, 3, min_tokens_to_keep=1).numpy(), g["tied_top3"])
+    np.testing.assert_array_equal(oracle.top_k_sampling(tied, 2, min_tokens_to_keep=8).numpy(), g["tied_top2_min8"])
+    np.testing.assert_array_equal(oracle.top_k_sampling(tied, 0, min_tokens_to_keep=8).numpy(), g["tied_top0"])
+    np.testing.assert_array_equal(oracle.get_sparse_emb(g["out_f32"], True, True, 20, 8).numpy(), g["topk20"])
+
+
+def test_quantiser_matches_reference_torch_twin(golden_dir):
+    g = _load(golden_dir, "quantize.npz")
+    assert oracle.quantize_reps(g["reps"], 100) == json.loads(str(g["json"]))
+
+
+def test_fusion_and_heap_match_reference(golden_dir):
+    with open(os.path.join(golden_dir, "fusion.json")) as f:
+        g = json.load(f)
+    lin = oracle.fuse_linear([g["dense"], g["sparse"]], weights=[0.7, 0.3])
+    rrf = oracle.fuse_rrf([g["dense"], g["sparse"]])
+    for q in g["linear"]:
+        assert lin[q].keys() == g["linear"][q].keys()
+        for p in lin[q]:
+            assert abs(lin[q][p] - g["linear"][q][p]) < 1e-12
+            assert abs(rrf[q][p] - g["rrf"][q][p]) < 1e-12
+    heaps = {}
+    for ch in g["chunks"]:
+        oracle.add_to_heap(ch, heaps, 7)
+    assert {q: sorted([s, p] for s, p in v) for q, v in heaps.items()} == g["heap_top7"]
+
+
+def test_merge_of_chunk_topk_equals_full_topk():
+    rng = np.random.default_rng(0)
+    q = rng.standard_normal((9, 24)).astype(np.float32)
+    c = rng.standard_normal((500, 24)).astype(np.float32)
+    c[100:110] = c[7]
+    full_s, full_i = oracle.flatip_topk(q, c, 40)
+    parts = [oracle.flatip_topk(q, c[lo:lo + 130], 40, id_offset=lo) for lo in range(0, 500, 130)]
+    ms, mi = oracle.merge_topk([p[0] for p in parts], [p[1] for p in parts], 40)
+    np.testing.assert_array_equal(mi, full_i)
+    np.testing.assert_array_equal(ms, full_s)
+    # key round trip preserves (score desc, id asc)
+    keys = oracle.encode_keys(full_s, full_i)
+    assert (np.diff(keys.astype(np.float64), axis=1) <= 0).all()
+    ds, di = oracle.decode_keys(keys)
+    np.testing.assert_array_equal(ds, full_s)
+    np.testing.assert_array_equal(di, full_i)
+    fs, fi = oracle.flatip_topk_fast(q, c, 40)
+    np.testing.assert_allclose(fs.numpy(), full_s, rtol=1e-6)
+
+
+def test_impact_formula_matches_notebook_definition():
+    # compute_similarity of scripts/asymmetric_sparse_infer.ipynb:207-228: sum over shared tokens of q[t]*d[t]
+    docs = [{1: 300, 2: 50}, {2: 10}, {}, {5: 700, 1: 1}]
+    qs = [{1: 2, 2: 1}, {9: 1}, {5: 1, 1: 1}]
+    S = oracle.impact_scores(qs, docs)
+    assert S.tolist() == [[650, 10, 0, 2], [0, 0, 0, 0], [300, 0, 0, 701]]
+    s, i = oracle.impact_topk(qs, docs, 3)
+    assert i.tolist() == [[0, 1, 3], [-1, -1, -1], [3, 0, -1]]
+    assert oracle.query_counts([4, 4, 9], "sum") == {4: 2, 9: 1} and oracle.query_counts([4, 4, 9], "bow") == {4: 1, 9: 1}
