@@ -258,6 +258,8 @@ def run_b200(args):
         res = search_step(*dev_batches[s % n_batches])
         sev[s + 1].record()
     lib.lr_set_profile_events(None, None)
+    plan = (ctypes.c_int64 * 8)()
+    lib.lr_flatip_last_plan(plan)
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
@@ -312,8 +314,6 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
-        plan = (ctypes.c_int64 * 8)()
-        lib.lr_flatip_last_plan(plan)
         n_local = hi - lo
         flops = 2.0 * Q * n_local * d
         ach = flops / (kern_ms_mean * 1e-3) / 1e12

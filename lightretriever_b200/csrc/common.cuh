@@ -155,6 +155,24 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each destination's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // createpolicy constants (same encodings CUTLASS uses for TMA::CacheHintSm90)
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t L2_EVICT_FIRST  = 0x12F0000000000000ull;
@@ -187,6 +205,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // 32 lanes x 32 consecutive f32 columns: thread i of the warp receives lane (taddr.lane + i)
+// same, arriving on the barrier at this offset in every CTA of `mask` (a slot shared through multicast is free only
+// when all CTAs of the cluster have read it)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

@@ -10,6 +10,7 @@
 namespace lr {
 
 struct FlatipPlan {
+  int cl, m_groups;
   int m_tiles, n_tiles, splits, band_size, n_bands, cap, grid, units, rounds;
   int64_t q_pad;
   size_t off_gthr, off_counts, off_cand, total_bytes;
@@ -17,8 +18,10 @@ struct FlatipPlan {
 
 static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   FlatipPlan pl{};
-  const int G = sm_count();
-  pl.m_tiles = int((Q + BM - 1) / BM);
+  const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), env_int("LR_FLATIP_CLUSTER", 0));
+  const int G = geo.n_clusters;  // clusters that run concurrently
+  pl.cl = geo.cl; pl.m_groups = geo.m_groups;
+  pl.m_tiles = geo.m_tiles;
   pl.n_tiles = int((N + BN - 1) / BN);
   pl.q_pad = int64_t(pl.m_tiles) * BM;
   int cap = 2 * k > k + 64 ? 2 * k : k + 64;
@@ -34,7 +37,7 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   double best = 1e300;
   int best_s = 1;
   for (int64_t s = 1; s <= s_max; ++s) {
-    const int64_t units = int64_t(pl.m_tiles) * s;
+    const int64_t units = int64_t(pl.m_groups) * s;
     const int64_t rounds = (units + G - 1) / G;
     const int64_t tiles = (pl.n_tiles + s - 1) / s;
     const double cost = double(rounds) * double(tiles + 1);  // +1: per-unit start-up
@@ -45,11 +48,12 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   }
   if (forced > 0 && forced <= pl.n_tiles) best_s = forced;
   pl.splits = best_s;
-  plan_bands(pl.m_tiles, env_int("LR_FLATIP_BAND", 32), pl.band_size, pl.n_bands);
-  pl.units = pl.m_tiles * pl.splits;
-  pl.grid = pl.units < G ? pl.units : G;
-  if (pl.grid < 1) pl.grid = 1;
-  pl.rounds = (pl.units + pl.grid - 1) / pl.grid;
+  pl.band_size = geo.band_size; pl.n_bands = geo.n_bands;
+  pl.units = pl.m_groups * pl.splits;
+  int clusters = pl.units < G ? pl.units : G;
+  if (clusters < 1) clusters = 1;
+  pl.grid = clusters * pl.cl;
+  pl.rounds = (pl.units + clusters - 1) / clusters;
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   pl.off_gthr = 0;
   pl.off_counts = align(pl.off_gthr + size_t(pl.q_pad) * 4);
@@ -77,7 +81,7 @@ static int check_flatip_args(const void* q, int64_t ldq, const void* corpus, int
 static void fill_params(GemmParams& prm, const FlatipPlan& pl, int64_t Q, int64_t N, int64_t d_used) {
   prm.rows = Q; prm.cols = N; prm.row_pad = pl.q_pad;
   prm.kblocks = int((d_used + BK - 1) / BK);
-  prm.m_tiles = pl.m_tiles; prm.n_tiles = pl.n_tiles; prm.splits = pl.splits;
+  prm.m_tiles = pl.m_tiles; prm.m_groups = pl.m_groups; prm.n_tiles = pl.n_tiles; prm.splits = pl.splits;
   prm.band_size = pl.band_size; prm.n_bands = pl.n_bands; prm.units = pl.units;
 }
 
@@ -92,7 +96,7 @@ extern "C" size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k) {
 
 extern "C" int lr_flatip_last_plan(int64_t* out8) {
   const FlatipPlan& pl = g_last_plan;
-  out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.splits; out8[3] = pl.band_size;
+  out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.splits; out8[3] = pl.band_size * pl.cl;
   out8[4] = pl.cap; out8[5] = pl.grid; out8[6] = pl.units; out8[7] = pl.rounds;
   return LR_OK;
 }
@@ -116,7 +120,7 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap(&tmA, q, Q, d_used, ldq, BM))) return rc;
-  if ((rc = make_tmap(&tmB, corpus, N, d_used, ldc, BN))) return rc;
+  if ((rc = make_tmap(&tmB, corpus, N, d_used, ldc, BN / pl.cl))) return rc;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   GemmParams prm{};
   fill_params(prm, pl, Q, N, d_used);
@@ -126,7 +130,9 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   LR_CUDA(cudaMemsetAsync(prm.gthr, 0, size_t(pl.q_pad) * 4, st));
-  if ((rc = launch_umma_gemm<EPI_TOPK>(tmA, tmB, prm, pl.grid, st))) return rc;
+  rc = pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2>(tmA, tmB, prm, pl.grid, st)
+                  : launch_umma_gemm<EPI_TOPK, 1>(tmA, tmB, prm, pl.grid, st);
+  if (rc) return rc;
   return lr_topk_merge(prm.cand, prm.counts, pl.splits, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, id_offset, out_scores,
                        out_ids, out_keys, stream);
 }
@@ -140,9 +146,10 @@ extern "C" int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap(&tmA, q, Q, d_used, ldq, BM))) return rc;
-  if ((rc = make_tmap(&tmB, corpus, N, d_used, ldc, BN))) return rc;
+  if ((rc = make_tmap(&tmB, corpus, N, d_used, ldc, BN / pl.cl))) return rc;
   GemmParams prm{};
   fill_params(prm, pl, Q, N, d_used);
   prm.dbg_scores = out_scores;
-  return launch_umma_gemm<EPI_STORE>(tmA, tmB, prm, pl.grid, st);
+  return pl.cl == 2 ? launch_umma_gemm<EPI_STORE, 2>(tmA, tmB, prm, pl.grid, st)
+                    : launch_umma_gemm<EPI_STORE, 1>(tmA, tmB, prm, pl.grid, st);
 }

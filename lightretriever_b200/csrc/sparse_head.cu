@@ -163,11 +163,12 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   int rc;
+  const GemmGeometry geo = plan_geometry(V, env_int("LR_SPARSE_HEAD_BAND", 12), env_int("LR_SPARSE_HEAD_CLUSTER", 0));
   if ((rc = make_tmap(&tmA, W, V, d, d, BM))) return rc;
-  if ((rc = make_tmap(&tmB, hidden, B * S, d, d, BN))) return rc;
+  if ((rc = make_tmap(&tmB, hidden, B * S, d, d, BN / geo.cl))) return rc;
   GemmParams prm{};
   prm.rows = V; prm.cols = B * S;
-  prm.m_tiles = int((V + BM - 1) / BM);
+  prm.m_tiles = geo.m_tiles; prm.m_groups = geo.m_groups;
   prm.row_pad = int64_t(prm.m_tiles) * BM;
   prm.kblocks = int((d + BK - 1) / BK);
   prm.seg_len = S; prm.n_segs = B;
@@ -178,12 +179,13 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   if (sps > B) sps = int(B);
   prm.segs_per_split = sps;
   prm.splits = int((B + sps - 1) / sps);
-  plan_bands(prm.m_tiles, env_int("LR_SPARSE_HEAD_BAND", 12), prm.band_size, prm.n_bands);
-  prm.units = prm.m_tiles * prm.splits;
+  prm.band_size = geo.band_size; prm.n_bands = geo.n_bands;
+  prm.units = prm.m_groups * prm.splits;
   prm.bias = bias; prm.mask = mask; prm.out = out; prm.relu = relu; prm.log1p = log1p;
-  const int G = sm_count();
-  const int grid = prm.units < G ? prm.units : G;
-  return launch_umma_gemm<EPI_MAXTOK>(tmA, tmB, prm, grid, st);
+  const int clusters = prm.units < geo.n_clusters ? prm.units : geo.n_clusters;
+  const int grid = clusters * geo.cl;
+  return geo.cl == 2 ? launch_umma_gemm<EPI_MAXTOK, 2>(tmA, tmB, prm, grid, st)
+                     : launch_umma_gemm<EPI_MAXTOK, 1>(tmA, tmB, prm, grid, st);
 }
 
 extern "C" size_t lr_sparsify_scratch_bytes(int64_t B, int64_t V) {

@@ -50,7 +50,8 @@ enum { EPI_STORE = 0, EPI_TOPK = 1, EPI_MAXTOK = 2 };
 struct GemmParams {
   int64_t rows, cols, row_pad;  // rows of A (queries / vocab), rows of B (documents / tokens)
   int kblocks;
-  int m_tiles, splits, band_size, n_bands, units;
+  int m_tiles, splits, band_size, n_bands, units;  // band_size / n_bands / units count GROUPS of CL row tiles
+  int m_groups;                                    // ceil(m_tiles / CL): one group per cluster
   // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
   int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range
   int64_t seg_len;      // EPI_MAXTOK: tokens per document (S); split = segs_per_split documents
@@ -72,14 +73,15 @@ struct GemmParams {
   int relu, log1p;
 };
 
-__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& m_tile, int& split) {
+// unit u -> (group of CL row tiles, column split)
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& m_group, int& split) {
   const int per_band = p.band_size * p.splits;
   int b = u / per_band;
   if (b > p.n_bands - 1) b = p.n_bands - 1;
   const int rem = u - b * per_band;
-  const int mb = min(p.band_size, p.m_tiles - b * p.band_size);
+  const int mb = min(p.band_size, p.m_groups - b * p.band_size);
   split = rem / mb;
-  m_tile = b * p.band_size + rem % mb;
+  m_group = b * p.band_size + rem % mb;
 }
 // columns [c0, c1) covered by a split; tiles start at c0 and step BN
 template <int EPI>
@@ -181,7 +183,10 @@ static __device__ __noinline__ uint32_t warp_compact_topk(uint64_t* buf, int n, 
 
 constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
 
-template <int EPI>
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs own adjacent row tiles of the same column split; each
+// loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, so the L2 -> SM
+// traffic per CTA and k-block drops from 48 KB to 32 KB.  tmB's box then holds BN / CL rows.
+template <int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -201,13 +206,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = (CL > 1) ? int(cluster_ctarank()) : 0;
+  const int cluster_id = int(blockIdx.x) / CL;
+  const int n_clusters = int(gridDim.x) / CL;
+  constexpr uint16_t kMcMask = uint16_t((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);  // every CTA of the cluster must have consumed the slot
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -221,6 +230,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -229,10 +239,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        int m_tile, split;
+      for (int u = cluster_id; u < p.units; u += n_clusters) {
+        int m_group, split;
         int64_t c0, c1;
-        decode_unit(p, u, m_tile, split);
+        decode_unit(p, u, m_group, split);
+        const int m_tile = m_group * CL + cta_rank;  // may be a padding tile (>= m_tiles): TMA zero-fills it
         split_cols<EPI>(p, split, c0, c1);
         for (int64_t cb = c0; cb < c1; cb += BN) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -240,7 +251,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(a_dst, &tmA, kb * BK, m_tile * BM, full_bar(stage));
-            tma_load_2d(a_dst + A_BYTES, &tmB, kb * BK, int(cb), full_bar(stage));
+            if (CL == 1) {
+              tma_load_2d(a_dst + A_BYTES, &tmB, kb * BK, int(cb), full_bar(stage));
+            } else {
+              // my half of the B tile, delivered to both CTAs (same offsets, each CTA's own full barrier)
+              tma_load_2d_mc(a_dst + A_BYTES + cta_rank * (B_BYTES / CL), &tmB, kb * BK,
+                             int(cb) + cta_rank * (BN / CL), full_bar(stage), kMcMask);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -257,10 +274,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        int m_tile, split;
+      for (int u = cluster_id; u < p.units; u += n_clusters) {
+        int m_group, split;
         int64_t c0, c1;
-        decode_unit(p, u, m_tile, split);
+        decode_unit(p, u, m_group, split);
         split_cols<EPI>(p, split, c0, c1);
         for (int64_t cb = c0; cb < c1; cb += BN) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -278,7 +295,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc,
                         (kb | kk) != 0 ? 1u : 0u);
             }
-            umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
+            // the smem slot is free once these MMAs have read it — in every CTA the multicast writes to
+            if (CL == 1) umma_commit(empty_bar(stage));
+            else umma_commit_mc(empty_bar(stage), kMcMask);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -300,13 +319,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t full = 0xFFFFFFFFu;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-      int m_tile, split;
+    for (int u = cluster_id; u < p.units; u += n_clusters) {
+      int m_group, split;
       int64_t c0, c1;
-      decode_unit(p, u, m_tile, split);
+      decode_unit(p, u, m_group, split);
+      const int m_tile = m_group * CL + cta_rank;
       split_cols<EPI>(p, split, c0, c1);
       const int64_t row = int64_t(m_tile) * BM + row_in_tile;
       const bool row_valid = row < p.rows;
+      const bool tile_valid = m_tile < p.m_tiles;  // false only for the padding tile of an odd last group
       // EPI_TOPK per-row running state
       uint64_t* buf = nullptr;
       uint32_t cnt = 0;
@@ -316,7 +337,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float run_max = BF16_LOWEST;
       float bias_v = 0.0f;
       int64_t seg = 0, seg_end = 0;
-      if (EPI == EPI_TOPK) {
+      if (EPI == EPI_TOPK && tile_valid) {
         buf = p.cand + (int64_t(split) * p.row_pad + row) * p.cap;
         if (row_valid && p.q_scale) qs = p.q_scale[row];
       }
@@ -411,7 +432,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           acc_phase ^= 1u;
         }
       }
-      if (EPI == EPI_TOPK) p.counts[int64_t(split) * p.row_pad + row] = row_valid ? int32_t(cnt) : 0;
+      if (EPI == EPI_TOPK && tile_valid) p.counts[int64_t(split) * p.row_pad + row] = row_valid ? int32_t(cnt) : 0;
       if (EPI == EPI_MAXTOK && c1 > c0) {
         float x = run_max;
         if (p.relu) x = fmaxf(x, 0.0f);
@@ -423,6 +444,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -486,21 +508,53 @@ struct ProfileEvents {
 };
 ProfileEvents& profile_events();  // thread-local, defined in api.cu
 
-template <int EPI>
+template <int EPI, int CL>
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       GEMM_SMEM_TOTAL);
+  auto kern = umma_gemm_kernel<EPI, CL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
     return LR_ECUDA;
   }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   ProfileEvents& pe = profile_events();
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.begin, st));
-  umma_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, st>>>(tmA, tmB, prm);
-  LR_LAUNCH_CHECK();
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, prm);
+  if (e != cudaSuccess) {
+    set_error("kernel launch failed: %s (grid=%d cluster=%d)", cudaGetErrorString(e), grid, CL);
+    return LR_ECUDA;
+  }
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
   return LR_OK;
+}
+
+// Work plan shared by the hosts of K2 and K3: groups of CL row tiles, bands of groups, grid of whole clusters.
+struct GemmGeometry {
+  int cl, m_tiles, m_groups, band_size, n_bands, n_clusters;
+};
+inline GemmGeometry plan_geometry(int64_t rows, int band_max_tiles, int force_cl) {
+  GemmGeometry g{};
+  g.m_tiles = int((rows + BM - 1) / BM);
+  g.cl = (g.m_tiles >= 2) ? 2 : 1;
+  if (force_cl == 1 || force_cl == 2) g.cl = force_cl;
+  g.m_groups = (g.m_tiles + g.cl - 1) / g.cl;
+  int band_max = band_max_tiles / g.cl;
+  plan_bands(g.m_groups, band_max < 1 ? 1 : band_max, g.band_size, g.n_bands);
+  g.n_clusters = sm_count() / g.cl;
+  if (g.n_clusters < 1) g.n_clusters = 1;
+  return g;
 }
 
 }  // namespace lr
