@@ -212,7 +212,7 @@ def run_b200(args):
         a, b = max(c0, lo), min(c0 + CHUNK_ROWS, hi)
         corpus[a - lo:b - lo] = blk[a - c0:b - c0]
         del blk
-    n_batches = 4
+    n_batches = 1 if os.environ.get('LR_BENCH_SAME_BATCH') else 4
     host_batches = []
     for i in range(n_batches):
         ids, offs = make_queries(Q, seed=100 + i)

@@ -24,12 +24,18 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   pl.m_tiles = geo.m_tiles;
   pl.n_tiles = int((N + BN - 1) / BN);
   pl.q_pad = int64_t(pl.m_tiles) * BM;
+  // Candidate-list capacity.  The running threshold of a row only rises when its list is cut back to the top-k, so
+  // between two cuts exactly cap-k entries are admitted and the number of documents consumed grows by cap/k per cut;
+  // measured on B200 (profiles/): 2k..2.5k beats both smaller and larger lists.
   int cap = 2 * k > k + 64 ? 2 * k : k + 64;
+  if (k <= 128 && cap < 256) cap = 256;
+  cap = env_int("LR_FLATIP_CAP", cap);
+  if (cap < k + 64) cap = k + 64;
   pl.cap = (cap + 63) / 64 * 64;
   // corpus splits: minimise rounds * tiles-per-unit; accept a larger split count only for a >0.5% gain
   const int64_t list_bytes = pl.q_pad * int64_t(pl.cap) * 8;
   int64_t s_max = int64_t(4) * G;
-  const int64_t mem_cap = (int64_t(8) << 30) / (list_bytes > 0 ? list_bytes : 1);
+  const int64_t mem_cap = (int64_t(12) << 30) / (list_bytes > 0 ? list_bytes : 1);
   if (s_max > mem_cap) s_max = mem_cap;
   if (s_max > pl.n_tiles) s_max = pl.n_tiles;
   if (s_max < 1) s_max = 1;
@@ -83,6 +89,9 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, int64_t Q, int64_
   prm.kblocks = int((d_used + BK - 1) / BK);
   prm.m_tiles = pl.m_tiles; prm.m_groups = pl.m_groups; prm.n_tiles = pl.n_tiles; prm.splits = pl.splits;
   prm.band_size = pl.band_size; prm.n_bands = pl.n_bands; prm.units = pl.units;
+  prm.policy_a = l2_policy(env_int("LR_FLATIP_POLICY_A", 0));
+  prm.policy_b = l2_policy(env_int("LR_FLATIP_POLICY_B", 0));
+  prm.debug_flags = env_int("LR_FLATIP_DEBUG", 0);
 }
 
 }  // namespace lr
@@ -129,7 +138,8 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   prm.gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
   prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
-  LR_CUDA(cudaMemsetAsync(prm.gthr, 0, size_t(pl.q_pad) * 4, st));
+  if (!(prm.debug_flags & 2))  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)
+    LR_CUDA(cudaMemsetAsync(prm.gthr, 0, size_t(pl.q_pad) * 4, st));
   rc = pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2>(tmA, tmB, prm, pl.grid, st)
                   : launch_umma_gemm<EPI_TOPK, 1>(tmA, tmB, prm, pl.grid, st);
   if (rc) return rc;

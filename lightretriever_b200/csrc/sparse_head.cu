@@ -182,6 +182,8 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   prm.band_size = geo.band_size; prm.n_bands = geo.n_bands;
   prm.units = prm.m_groups * prm.splits;
   prm.bias = bias; prm.mask = mask; prm.out = out; prm.relu = relu; prm.log1p = log1p;
+  prm.policy_a = l2_policy(env_int("LR_SPARSE_HEAD_POLICY_A", 0));
+  prm.policy_b = l2_policy(env_int("LR_SPARSE_HEAD_POLICY_B", 0));
   const int clusters = prm.units < geo.n_clusters ? prm.units : geo.n_clusters;
   const int grid = clusters * geo.cl;
   return geo.cl == 2 ? launch_umma_gemm<EPI_MAXTOK, 2>(tmA, tmB, prm, grid, st)

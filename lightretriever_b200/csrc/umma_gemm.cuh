@@ -52,6 +52,8 @@ struct GemmParams {
   int kblocks;
   int m_tiles, splits, band_size, n_bands, units;  // band_size / n_bands / units count GROUPS of CL row tiles
   int m_groups;                                    // ceil(m_tiles / CL): one group per cluster
+  uint64_t policy_a, policy_b;                     // L2 eviction policy of the A (row) and B (column) tile loads
+  int debug_flags;                                 // bit 0: epilogue drops every score (main-loop-only timing)
   // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
   int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range
   int64_t seg_len;      // EPI_MAXTOK: tokens per document (S); split = segs_per_split documents
@@ -250,13 +252,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(a_dst, &tmA, kb * BK, m_tile * BM, full_bar(stage));
+            tma_load_2d_hint(a_dst, &tmA, kb * BK, m_tile * BM, full_bar(stage), p.policy_a);
             if (CL == 1) {
-              tma_load_2d(a_dst + A_BYTES, &tmB, kb * BK, int(cb), full_bar(stage));
+              tma_load_2d_hint(a_dst + A_BYTES, &tmB, kb * BK, int(cb), full_bar(stage), p.policy_b);
             } else {
               // my half of the B tile, delivered to both CTAs (same offsets, each CTA's own full barrier)
-              tma_load_2d_mc(a_dst + A_BYTES + cta_rank * (B_BYTES / CL), &tmB, kb * BK,
-                             int(cb) + cta_rank * (BN / CL), full_bar(stage), kMcMask);
+              tma_load_2d_mc_hint(a_dst + A_BYTES + cta_rank * (B_BYTES / CL), &tmB, kb * BK,
+                                  int(cb) + cta_rank * (BN / CL), full_bar(stage), kMcMask, p.policy_b);
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -353,6 +355,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t g = ld_relaxed_u32(p.gthr + row);
           const float tg = (g <= KEY_NEG_INF) ? -INFINITY : key_to_f32(g - 1u);  // s >= gthr  <=>  s > tg
           thr = fmaxf(thr_local, tg);
+          if (p.debug_flags & 1) thr = INFINITY;
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
@@ -538,6 +541,10 @@ inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   }
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
   return LR_OK;
+}
+
+inline uint64_t l2_policy(int code) {
+  return code == 1 ? L2_EVICT_FIRST : code == 2 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
 }
 
 // Work plan shared by the hosts of K2 and K3: groups of CL row tiles, bands of groups, grid of whole clusters.
