@@ -326,13 +326,13 @@ def run_b200(args):
             "p50_ms_per_batch": statistics.median(step_ms),
             "e2e": {"value": Q * args.steps / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * (3 if world == 1 else 4),
+            "gpu_launches": args.steps * ((3 if world == 1 else 4) + (3 if plan[7] > 0 else 0)),
             "roofline": {"kernel": "umma_gemm_kernel<EPI_TOPK> (tcgen05 bf16 GEMM + fused top-k epilogue)",
                          "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                          "flop_per_launch": flops, "kernel_ms": kern_ms_mean, "traffic": None,
                          "kernel_share_of_step": kern_ms_mean / (total_ms / args.steps)},
-            "plan": dict(zip(["m_tiles", "n_tiles", "splits", "band", "cap", "grid", "units", "rounds"], list(plan))),
+            "plan": dict(zip(["m_tiles", "n_tiles", "splits", "band", "cap", "grid", "units", "prefix_tiles"], list(plan))),
             "parity_spot_check": {"queries": nchk, "ids_identical_to_torch_fp32_topk": ids_same, "max_abs_score_err": score_err},
             "clocks": clocks,
         }

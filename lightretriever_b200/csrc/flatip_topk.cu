@@ -1,27 +1,71 @@
-// flatip_topk.cu — K2: exact flat inner-product top-k on B200 (host side: plan, tensor maps, launch).
+// flatip_topk.cu — K2: exact flat inner-product top-k on B200 (host side: plan, tensor maps, launches).
 //
 // Replaces faiss.IndexFlatIP.search as called by FaissIndex.search
 // (reference retriever/faiss_index.py:27-40) plus the per-chunk heap merge
 // (retriever/hybrid_search.py:182-205).  The kernel is umma_gemm_kernel<EPI_TOPK> in umma_gemm.cuh:
 // rows = queries, columns = documents, the epilogue keeps per-(split, query) candidate lists which
-// lr_topk_merge reduces to the final sorted top-k.
+// topk_merge reduces to the final sorted top-k.
+//
+// Large searches run in two phases.  Phase A scores a short corpus prefix and seeds every query's running
+// threshold with its k-th best score there (any k documents give a valid lower bound of the final k-th score);
+// phase B scores the rest with warm thresholds, so almost nothing is appended to the candidate lists and the
+// list compactions that would stall the MMA pipe (and desynchronise the CTAs that share corpus tiles in L2)
+// all but disappear.  The prefix's own top-k joins the final merge as one more candidate list.
 #include "umma_gemm.cuh"
 
 namespace lr {
 
-struct FlatipPlan {
-  int cl, m_groups;
-  int m_tiles, n_tiles, splits, band_size, n_bands, cap, grid, units, rounds;
-  int64_t q_pad;
-  size_t off_gthr, off_counts, off_cand, total_bytes;
+int topk_merge_strided(const uint64_t* keys, const int32_t* counts, int L, int64_t Q, int64_t q_stride, int cap, int k,
+                       int score_kind, int64_t id_offset, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                       int64_t out_key_stride, cudaStream_t st);
+
+struct PassPlan {
+  int tile_begin, tile_end, splits, units, grid, rounds;
 };
+struct FlatipPlan {
+  int cl, m_groups, m_tiles, n_tiles, band_size, n_bands, cap, n_clusters;
+  int64_t q_pad;
+  PassPlan main, prefix;  // prefix.units == 0 -> single phase
+  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, total_bytes;
+};
+
+// corpus splits of one pass: minimise rounds * tiles-per-unit; accept a larger split count only for a >0.5% gain
+static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile_end, int64_t s_cap, int forced) {
+  PassPlan pp{};
+  pp.tile_begin = tile_begin;
+  pp.tile_end = tile_end;
+  const int nt = tile_end - tile_begin;
+  int64_t s_max = int64_t(4) * n_clusters;
+  if (s_max > s_cap) s_max = s_cap;
+  if (s_max > nt) s_max = nt;
+  if (s_max < 1) s_max = 1;
+  double best = 1e300;
+  int best_s = 1;
+  for (int64_t s = 1; s <= s_max; ++s) {
+    const int64_t units = int64_t(m_groups) * s;
+    const int64_t rounds = (units + n_clusters - 1) / n_clusters;
+    const int64_t tiles = (nt + s - 1) / s;
+    const double cost = double(rounds) * double(tiles + 1);  // +1: per-unit start-up
+    if (cost < best * (1.0 - 0.005)) {
+      best = cost;
+      best_s = int(s);
+    }
+  }
+  if (forced > 0 && forced <= nt) best_s = forced;
+  pp.splits = best_s;
+  pp.units = m_groups * pp.splits;
+  int clusters = pp.units < n_clusters ? pp.units : n_clusters;
+  if (clusters < 1) clusters = 1;
+  pp.grid = clusters;  // in clusters; multiplied by cl at launch
+  pp.rounds = (pp.units + clusters - 1) / clusters;
+  return pp;
+}
 
 static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   FlatipPlan pl{};
   const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), env_int("LR_FLATIP_CLUSTER", 0));
-  const int G = geo.n_clusters;  // clusters that run concurrently
-  pl.cl = geo.cl; pl.m_groups = geo.m_groups;
-  pl.m_tiles = geo.m_tiles;
+  pl.cl = geo.cl; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
+  pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;
   pl.n_tiles = int((N + BN - 1) / BN);
   pl.q_pad = int64_t(pl.m_tiles) * BM;
   // Candidate-list capacity.  The running threshold of a row only rises when its list is cut back to the top-k, so
@@ -32,39 +76,32 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   cap = env_int("LR_FLATIP_CAP", cap);
   if (cap < k + 64) cap = k + 64;
   pl.cap = (cap + 63) / 64 * 64;
-  // corpus splits: minimise rounds * tiles-per-unit; accept a larger split count only for a >0.5% gain
   const int64_t list_bytes = pl.q_pad * int64_t(pl.cap) * 8;
-  int64_t s_max = int64_t(4) * G;
-  const int64_t mem_cap = (int64_t(12) << 30) / (list_bytes > 0 ? list_bytes : 1);
-  if (s_max > mem_cap) s_max = mem_cap;
-  if (s_max > pl.n_tiles) s_max = pl.n_tiles;
-  if (s_max < 1) s_max = 1;
-  const int forced = env_int("LR_FLATIP_SPLITS", 0);
-  double best = 1e300;
-  int best_s = 1;
-  for (int64_t s = 1; s <= s_max; ++s) {
-    const int64_t units = int64_t(pl.m_groups) * s;
-    const int64_t rounds = (units + G - 1) / G;
-    const int64_t tiles = (pl.n_tiles + s - 1) / s;
-    const double cost = double(rounds) * double(tiles + 1);  // +1: per-unit start-up
-    if (cost < best * (1.0 - 0.005)) {
-      best = cost;
-      best_s = int(s);
-    }
+  const int64_t s_cap = (int64_t(12) << 30) / (list_bytes > 0 ? list_bytes : 1);
+
+  // Phase A (warm start) when the search is compute-bound and long enough to amortise it.  Measured on the 1.1M x 4096
+  // shard shape (profiles/k2_schedule_sweeps_r1.md): a 32768-document prefix brings the main pass within 2% of a run
+  // with perfect thresholds; 4k..8k-document prefixes do not pay for themselves.
+  int prefix_tiles = 0;
+  const int want = env_int("LR_FLATIP_PREFIX_DOCS", -1);
+  if (want != 0) {
+    int64_t docs = want > 0 ? want : 32768;
+    if (docs < 4 * int64_t(k)) docs = 4 * int64_t(k);
+    const int pt = int((docs + BN - 1) / BN);
+    const bool big_enough = want > 0 || (pl.m_groups >= 4 && pl.n_tiles >= 32 * pt);
+    if (big_enough && pt < pl.n_tiles) prefix_tiles = pt;
   }
-  if (forced > 0 && forced <= pl.n_tiles) best_s = forced;
-  pl.splits = best_s;
-  pl.band_size = geo.band_size; pl.n_bands = geo.n_bands;
-  pl.units = pl.m_groups * pl.splits;
-  int clusters = pl.units < G ? pl.units : G;
-  if (clusters < 1) clusters = 1;
-  pl.grid = clusters * pl.cl;
-  pl.rounds = (pl.units + clusters - 1) / clusters;
+  if (prefix_tiles > 0) pl.prefix = plan_pass(pl.m_groups, geo.n_clusters, 0, prefix_tiles, s_cap, 0);
+  pl.main = plan_pass(pl.m_groups, geo.n_clusters, prefix_tiles, pl.n_tiles, s_cap, env_int("LR_FLATIP_SPLITS", 0));
+
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+  const int main_lists = pl.main.splits + (prefix_tiles > 0 ? 1 : 0);  // + the prefix's merged top-k
   pl.off_gthr = 0;
-  pl.off_counts = align(pl.off_gthr + size_t(pl.q_pad) * 4);
-  pl.off_cand = align(pl.off_counts + size_t(pl.splits) * pl.q_pad * 4);
-  pl.total_bytes = align(pl.off_cand + size_t(pl.splits) * pl.q_pad * pl.cap * 8);
+  pl.off_counts = align(size_t(pl.q_pad) * 4);
+  pl.off_cand = align(pl.off_counts + size_t(main_lists) * pl.q_pad * 4);
+  pl.off_pcounts = align(pl.off_cand + size_t(main_lists) * pl.q_pad * pl.cap * 8);
+  pl.off_pcand = align(pl.off_pcounts + size_t(pl.prefix.splits) * pl.q_pad * 4);
+  pl.total_bytes = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.q_pad * pl.cap * 8);
   return pl;
 }
 
@@ -84,14 +121,37 @@ static int check_flatip_args(const void* q, int64_t ldq, const void* corpus, int
   return LR_OK;
 }
 
-static void fill_params(GemmParams& prm, const FlatipPlan& pl, int64_t Q, int64_t N, int64_t d_used) {
+static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& pp, int64_t Q, int64_t N, int64_t d_used) {
   prm.rows = Q; prm.cols = N; prm.row_pad = pl.q_pad;
   prm.kblocks = int((d_used + BK - 1) / BK);
-  prm.m_tiles = pl.m_tiles; prm.m_groups = pl.m_groups; prm.n_tiles = pl.n_tiles; prm.splits = pl.splits;
-  prm.band_size = pl.band_size; prm.n_bands = pl.n_bands; prm.units = pl.units;
+  prm.m_tiles = pl.m_tiles; prm.m_groups = pl.m_groups;
+  prm.tile_begin = pp.tile_begin; prm.n_tiles = pp.tile_end; prm.splits = pp.splits;
+  prm.band_size = pl.band_size; prm.n_bands = pl.n_bands; prm.units = pp.units;
   prm.policy_a = l2_policy(env_int("LR_FLATIP_POLICY_A", 0));
   prm.policy_b = l2_policy(env_int("LR_FLATIP_POLICY_B", 0));
   prm.debug_flags = env_int("LR_FLATIP_DEBUG", 0);
+}
+
+template <int EPI>
+static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                       const GemmParams& prm, cudaStream_t st) {
+  return pl.cl == 2 ? launch_umma_gemm<EPI, 2>(tmA, tmB, prm, pp.grid * 2, st)
+                    : launch_umma_gemm<EPI, 1>(tmA, tmB, prm, pp.grid, st);
+}
+
+// gthr[q] = score key of the prefix's k-th best document (0 when the prefix holds fewer than k documents);
+// counts of the extra merge list = k
+__global__ void seed_threshold_kernel(const uint64_t* __restrict__ prefix_keys, int64_t key_stride, int k, int64_t q_pad,
+                                      int64_t Q, uint32_t* __restrict__ gthr, int32_t* __restrict__ counts) {
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= q_pad) return;
+  uint32_t g = 0;
+  if (q < Q) {
+    const uint64_t kth = prefix_keys[q * key_stride + (k - 1)];
+    if (kth != 0ull) g = key_hi(kth);
+  }
+  gthr[q] = g;
+  counts[q] = q < Q ? k : 0;
 }
 
 }  // namespace lr
@@ -105,8 +165,8 @@ extern "C" size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k) {
 
 extern "C" int lr_flatip_last_plan(int64_t* out8) {
   const FlatipPlan& pl = g_last_plan;
-  out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.splits; out8[3] = pl.band_size * pl.cl;
-  out8[4] = pl.cap; out8[5] = pl.grid; out8[6] = pl.units; out8[7] = pl.rounds;
+  out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.main.splits; out8[3] = pl.band_size * pl.cl;
+  out8[4] = pl.cap; out8[5] = pl.main.grid * pl.cl; out8[6] = pl.main.units; out8[7] = pl.prefix.tile_end;
   return LR_OK;
 }
 
@@ -131,20 +191,44 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   if ((rc = make_tmap(&tmA, q, Q, d_used, ldq, BM))) return rc;
   if ((rc = make_tmap(&tmB, corpus, N, d_used, ldc, BN / pl.cl))) return rc;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint32_t* gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
+  int32_t* counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+  const bool two_phase = pl.prefix.units > 0;
+  const int debug = env_int("LR_FLATIP_DEBUG", 0);
+
   GemmParams prm{};
-  fill_params(prm, pl, Q, N, d_used);
   prm.k = k; prm.cap = pl.cap;
   prm.q_scale = q_scale; prm.c_scale = c_scale;
-  prm.gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
-  prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
-  prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
-  if (!(prm.debug_flags & 2))  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)
-    LR_CUDA(cudaMemsetAsync(prm.gthr, 0, size_t(pl.q_pad) * 4, st));
-  rc = pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2>(tmA, tmB, prm, pl.grid, st)
-                  : launch_umma_gemm<EPI_TOPK, 1>(tmA, tmB, prm, pl.grid, st);
-  if (rc) return rc;
-  return lr_topk_merge(prm.cand, prm.counts, pl.splits, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, id_offset, out_scores,
-                       out_ids, out_keys, stream);
+  prm.gthr = gthr;
+  const ProfileEvents pe_saved = profile_events();
+  if (two_phase) {
+    // ---- phase A: prefix -> its top-k lands in list slot `main.splits` of the main candidate array
+    profile_events() = ProfileEvents{};  // the profiling events bracket the main pass only
+    fill_params(prm, pl, pl.prefix, Q, N, d_used);
+    prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_pcounts);
+    prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_pcand);
+    LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
+    rc = launch_pass<EPI_TOPK>(pl, pl.prefix, tmA, tmB, prm, st);
+    uint64_t* slot = cand + size_t(pl.main.splits) * pl.q_pad * pl.cap;
+    if (!rc)
+      rc = topk_merge_strided(prm.cand, prm.counts, pl.prefix.splits, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0, nullptr,
+                              nullptr, slot, pl.cap, st);
+    profile_events() = pe_saved;
+    if (rc) return rc;
+    seed_threshold_kernel<<<unsigned((pl.q_pad + 255) / 256), 256, 0, st>>>(
+        slot, pl.cap, k, pl.q_pad, Q, gthr, counts + size_t(pl.main.splits) * pl.q_pad);
+    LR_LAUNCH_CHECK();
+  } else if (!(debug & 2)) {  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)
+    LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
+  }
+  // ---- phase B / single phase
+  fill_params(prm, pl, pl.main, Q, N, d_used);
+  prm.counts = counts;
+  prm.cand = cand;
+  if ((rc = launch_pass<EPI_TOPK>(pl, pl.main, tmA, tmB, prm, st))) return rc;
+  return topk_merge_strided(cand, counts, pl.main.splits + (two_phase ? 1 : 0), Q, pl.q_pad, pl.cap, k, LR_SCORE_F32,
+                            id_offset, out_scores, out_ids, out_keys, k, st);
 }
 
 extern "C" int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,
@@ -153,13 +237,13 @@ extern "C" int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, 
   if (rc) return rc;
   LR_CHECK_ARG(out_scores, "flatip_scores: null output");
   FlatipPlan pl = make_plan(Q, N, 1);
+  const PassPlan all = plan_pass(pl.m_groups, pl.n_clusters, 0, pl.n_tiles, 1 << 20, 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap(&tmA, q, Q, d_used, ldq, BM))) return rc;
   if ((rc = make_tmap(&tmB, corpus, N, d_used, ldc, BN / pl.cl))) return rc;
   GemmParams prm{};
-  fill_params(prm, pl, Q, N, d_used);
+  fill_params(prm, pl, all, Q, N, d_used);
   prm.dbg_scores = out_scores;
-  return pl.cl == 2 ? launch_umma_gemm<EPI_STORE, 2>(tmA, tmB, prm, pl.grid, st)
-                    : launch_umma_gemm<EPI_STORE, 1>(tmA, tmB, prm, pl.grid, st);
+  return launch_pass<EPI_STORE>(pl, all, tmA, tmB, prm, st);
 }

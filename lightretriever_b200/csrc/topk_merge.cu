@@ -20,6 +20,7 @@ struct MergeParams {
   int L;
   int64_t Q, q_stride;
   int cap, k, kpad, score_kind;
+  int64_t out_key_stride;  // row pitch of out_keys (>= k)
   int64_t id_offset;
   float* out_scores;
   int64_t* out_ids;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergePa
     if (p.out_scores)
       p.out_scores[o] = valid ? (p.score_kind == LR_SCORE_F32 ? key_to_f32(hi) : float(hi)) : -INFINITY;
     if (p.out_ids) p.out_ids[o] = valid ? id : int64_t(-1);
-    if (p.out_keys) p.out_keys[o] = valid ? make_key(hi, uint32_t(id)) : 0ull;
+    if (p.out_keys) p.out_keys[q * p.out_key_stride + i] = valid ? make_key(hi, uint32_t(id)) : 0ull;
   }
 }
 
@@ -170,6 +171,24 @@ __global__ void encode_keys_kernel(const float* scores, const int64_t* ids, int6
   if (i >= n) return;
   const int64_t id = ids[i];
   keys[i] = (id < 0 || id >= 0xFFFFFFFFll) ? 0ull : make_key(f32_to_key(scores[i]), uint32_t(id));
+}
+
+// internal entry: like lr_topk_merge, with a row pitch for out_keys (a merged list can be written straight into a
+// slot of another candidate-list array)
+int topk_merge_strided(const uint64_t* keys, const int32_t* counts, int L, int64_t Q, int64_t q_stride, int cap, int k,
+                       int score_kind, int64_t id_offset, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                       int64_t out_key_stride, cudaStream_t st) {
+  MergeParams p{};
+  p.keys = keys; p.counts = counts; p.L = L; p.Q = Q; p.q_stride = q_stride; p.cap = cap; p.k = k;
+  int kpad = 2;
+  while (kpad < k) kpad <<= 1;
+  p.kpad = kpad;
+  p.score_kind = score_kind; p.id_offset = id_offset;
+  p.out_scores = out_scores; p.out_ids = out_ids; p.out_keys = out_keys;
+  p.out_key_stride = out_key_stride;
+  topk_merge_kernel<<<unsigned(Q), MERGE_THREADS, size_t(kpad) * 8, st>>>(p);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
 }
 
 }  // namespace lr
@@ -185,17 +204,8 @@ extern "C" int lr_topk_merge(const uint64_t* keys, const int32_t* counts, int L,
   LR_CHECK_ARG(k >= 1 && k <= 4096, "topk_merge: k (%d) must be in [1, 4096]", k);
   LR_CHECK_ARG(score_kind == LR_SCORE_F32 || score_kind == LR_SCORE_U32, "topk_merge: bad score_kind %d", score_kind);
   LR_CHECK_ARG(id_offset >= 0, "topk_merge: negative id_offset");
-  MergeParams p{};
-  p.keys = keys; p.counts = counts; p.L = L; p.Q = Q; p.q_stride = q_stride; p.cap = cap; p.k = k;
-  int kpad = 2;
-  while (kpad < k) kpad <<= 1;
-  p.kpad = kpad;
-  p.score_kind = score_kind; p.id_offset = id_offset;
-  p.out_scores = out_scores; p.out_ids = out_ids; p.out_keys = out_keys;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  topk_merge_kernel<<<unsigned(Q), MERGE_THREADS, size_t(kpad) * 8, st>>>(p);
-  LR_LAUNCH_CHECK();
-  return LR_OK;
+  return topk_merge_strided(keys, counts, L, Q, q_stride, cap, k, score_kind, id_offset, out_scores, out_ids, out_keys, k,
+                            static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lr_encode_keys(const float* scores, const int64_t* ids, int64_t n, uint64_t* keys, void* stream) {

@@ -43,7 +43,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int ACC_STAGES = 2;
 constexpr int SMEM_BAR_BYTES = 256;
 constexpr int SMEM_HIST_BYTES = 4 * 256 * 4;
-constexpr int GEMM_SMEM_TOTAL = 1024 + STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES;
+constexpr int LIST_STAGE_ENTRIES = 768;  // per epilogue warp: a candidate list of <= 768 entries is compacted in smem
+constexpr int SMEM_LIST_BYTES = 4 * LIST_STAGE_ENTRIES * 8;
+constexpr int GEMM_SMEM_TOTAL = 1024 + STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_LIST_BYTES;
+static_assert(GEMM_SMEM_TOTAL <= 227 * 1024, "shared memory budget exceeded");
 
 enum { EPI_STORE = 0, EPI_TOPK = 1, EPI_MAXTOK = 2 };
 
@@ -55,7 +58,8 @@ struct GemmParams {
   uint64_t policy_a, policy_b;                     // L2 eviction policy of the A (row) and B (column) tile loads
   int debug_flags;                                 // bit 0: epilogue drops every score (main-loop-only timing)
   // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
-  int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range
+  int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range of [tile_begin, n_tiles)
+  int tile_begin;
   int64_t seg_len;      // EPI_MAXTOK: tokens per document (S); split = segs_per_split documents
   int64_t n_segs;
   int segs_per_split;
@@ -95,8 +99,9 @@ __device__ __forceinline__ void split_cols(const GemmParams& p, int split, int64
     c0 = s0 * p.seg_len;
     c1 = s1 * p.seg_len;
   } else {
-    const int64_t t0 = (int64_t(split) * p.n_tiles) / p.splits;
-    const int64_t t1 = (int64_t(split + 1) * p.n_tiles) / p.splits;
+    const int64_t nt = p.n_tiles - p.tile_begin;
+    const int64_t t0 = p.tile_begin + (int64_t(split) * nt) / p.splits;
+    const int64_t t1 = p.tile_begin + (int64_t(split + 1) * nt) / p.splits;
     c0 = t0 * BN;
     c1 = t1 * BN;
     if (c1 > p.cols) c1 = p.cols;
@@ -105,8 +110,17 @@ __device__ __forceinline__ void split_cols(const GemmParams& p, int split, int64
 
 // Cut a candidate list (n entries, ascending id order) back to its exact top-k, keeping id order.
 // Returns the score key of the k-th best entry.  All 32 lanes participate.
-static __device__ __noinline__ uint32_t warp_compact_topk(uint64_t* buf, int n, int k, uint32_t* hist, int lane) {
+// When the list fits the warp's shared-memory staging area it is pulled in with one coalesced sweep, the four radix
+// passes and the stable compaction run on shared memory, and only the survivors go back to global memory; otherwise
+// every pass re-reads the list from L2.
+static __device__ __noinline__ uint32_t warp_compact_topk(uint64_t* buf, int n, int k, uint32_t* hist,
+                                                          uint64_t* stage, int stage_cap, int lane) {
   const uint32_t full = 0xFFFFFFFFu;
+  const bool staged = n <= stage_cap;
+  if (staged) {
+    for (int i = lane; i < n; i += 32) stage[i] = ld_cg_u64(buf + i);
+    __syncwarp();
+  }
   uint32_t prefix = 0;
   uint32_t remaining = uint32_t(k);
 #pragma unroll 1
@@ -116,58 +130,27 @@ static __device__ __noinline__ uint32_t warp_compact_topk(uint64_t* buf, int n, 
     for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
-      const uint32_t h = key_hi(ld_cg_u64(buf + i));
+      const uint32_t h = key_hi(staged ? stage[i] : ld_cg_u64(buf + i));
       const bool match = (pass == 3) || ((h >> (shift + 8)) == prefix);
       if (match) atomicAdd(&hist[(h >> shift) & 0xFFu], 1u);
     }
     __syncwarp();
-    const int base = 8 * (31 - lane);  // lane 0 owns the highest bins
-    uint32_t c[8];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      c[i] = hist[base + 7 - i];
-      sum += c[i];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t t = __shfl_up_sync(full, incl, off);
-      if (lane >= off) incl += t;
-    }
-    const uint32_t excl = incl - sum;
-    const bool hit = (excl < remaining) && (remaining <= incl);
-    const uint32_t hm = __ballot_sync(full, hit);
-    const int src = hm ? (__ffs(hm) - 1) : 31;
-    uint32_t bin = 0, rem2 = 1;
-    if (lane == src) {
-      uint32_t acc = excl;
-      bool done = false;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (!done && acc + c[i] >= remaining) {
-          bin = uint32_t(base + 7 - i);
-          rem2 = remaining - acc;
-          done = true;
-        }
-        if (!done) acc += c[i];
-      }
-    }
-    bin = __shfl_sync(full, bin, src);
-    rem2 = __shfl_sync(full, rem2, src);
+    uint32_t bin, rem2;
+    bool take_all;
+    warp_find_bin_desc(hist, remaining, bin, rem2, take_all);
     prefix = (prefix << 8) | bin;
     remaining = rem2;
     __syncwarp();
   }
   const uint32_t vk = prefix;            // score key of the k-th best
   const uint32_t keep_ties = remaining;  // how many entries equal to vk survive (lowest ids first)
-  // stable in-place compaction (write index never passes the read index)
+  // stable compaction (in place: the write index never passes the read index)
   uint32_t out = 0, ties_seen = 0;
   const uint32_t lt = lanemask_lt();
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     const bool in = i < n;
-    const uint64_t key = in ? ld_cg_u64(buf + i) : 0ull;
+    const uint64_t key = in ? (staged ? stage[i] : ld_cg_u64(buf + i)) : 0ull;
     const uint32_t h = key_hi(key);
     const bool gt = in && h > vk;
     const bool eq = in && h == vk;
@@ -205,6 +188,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
   uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + SMEM_BAR_BYTES);
+  uint64_t* list_stage_all =
+      reinterpret_cast<uint64_t*>(smem_gen + STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -318,6 +303,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     uint32_t* hist = hist_all + (warp - 2) * 256;
+    uint64_t* list_stage = list_stage_all + (warp - 2) * LIST_STAGE_ENTRIES;
     const uint32_t full = 0xFFFFFFFFu;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -397,7 +383,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int n_r = __shfl_sync(full, int(cnt), r);
               const int64_t row_r = int64_t(m_tile) * BM + quarter * 32 + r;
               uint64_t* buf_r = p.cand + (int64_t(split) * p.row_pad + row_r) * p.cap;
-              const uint32_t vk = warp_compact_topk(buf_r, n_r, p.k, hist, lane);
+              const uint32_t vk = warp_compact_topk(buf_r, n_r, p.k, hist, list_stage, LIST_STAGE_ENTRIES, lane);
               if (lane == r) {
                 cnt = uint32_t(p.k);
                 thr_local = key_to_f32(vk);

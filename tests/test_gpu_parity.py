@@ -163,6 +163,33 @@ def test_flatip_adversarial_order_stays_exact():
     np.testing.assert_array_equal(_np(i), ei)
 
 
+@pytest.mark.parametrize("prefix_docs,cluster", [(512, 2), (2048, 1), (300, 2)])
+def test_flatip_two_phase_warm_start_is_exact(monkeypatch, prefix_docs, cluster):
+    """Phase A (corpus prefix seeds the thresholds, its top-k joins the merge) + phase B must equal the one-pass result,
+    including ties that straddle the prefix boundary and results that live entirely inside the prefix."""
+    monkeypatch.setenv("LR_FLATIP_PREFIX_DOCS", str(prefix_docs))
+    monkeypatch.setenv("LR_FLATIP_CLUSTER", str(cluster))
+    gen = torch.Generator().manual_seed(prefix_docs)
+    Q, N, d, k = 300, 30000, 128, 100
+    q = F.normalize(torch.randn(Q, d, generator=gen), dim=-1).bfloat16()
+    c = F.normalize(torch.randn(N, d, generator=gen), dim=-1).bfloat16()
+    c[prefix_docs - 3:prefix_docs + 3] = c[7]          # exact ties across the phase boundary
+    c[:50] = q[:50]                                    # best documents of the first queries sit in the prefix
+    s, i = lr.flatip_topk(q.cuda(), c.cuda(), k, id_offset=5)
+    es, ei = oracle.flatip_topk(q.float(), c.float(), k, id_offset=5)
+    ref = (q.float() @ c.float().T).numpy()
+    oracle.check_topk_parity(_np(s), _np(i), ref, k, rtol=1e-2, id_offset=5)
+    assert (ei == _np(i)).mean() > 0.999
+    # adversarial order (scores ascending with the id) under the two-phase plan
+    base = torch.zeros(20000, 64)
+    base[:, 0] = torch.linspace(0.1, 1.0, 20000)
+    qq = torch.zeros(2, 64)
+    qq[:, 0] = torch.tensor([1.0, -1.0])
+    s2, i2 = lr.flatip_topk(qq.bfloat16().cuda(), base.bfloat16().cuda(), 50)
+    _, ei2 = oracle.flatip_topk(qq.bfloat16().float(), base.bfloat16().float(), 50)
+    np.testing.assert_array_equal(_np(i2), ei2)
+
+
 def test_searcher_surface_matches_reference_protocol():
     gen = torch.Generator().manual_seed(4)
     corpus = F.normalize(torch.randn(600, 128, generator=gen), dim=-1)
