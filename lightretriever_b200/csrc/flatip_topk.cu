@@ -23,7 +23,7 @@ struct PassPlan {
   int tile_begin, tile_end, splits, units, grid, rounds;
 };
 struct FlatipPlan {
-  int cl, m_groups, m_tiles, n_tiles, band_size, n_bands, cap, n_clusters;
+  int cl, pair, m_groups, m_tiles, n_tiles, band_size, n_bands, cap, n_clusters;
   int64_t q_pad;
   PassPlan main, prefix;  // prefix.units == 0 -> single phase
   size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, total_bytes;
@@ -64,7 +64,7 @@ static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile
 static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   FlatipPlan pl{};
   const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), env_int("LR_FLATIP_CLUSTER", 0));
-  pl.cl = geo.cl; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
+  pl.cl = geo.cl; pl.pair = geo.pair; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
   pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;
   pl.n_tiles = int((N + BN - 1) / BN);
   pl.q_pad = int64_t(pl.m_tiles) * BM;
@@ -135,6 +135,7 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
 template <int EPI>
 static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const GemmParams& prm, cudaStream_t st) {
+  if (pl.pair) return launch_umma_gemm<EPI, 2, true>(tmA, tmB, prm, pp.grid * 2, st);
   return pl.cl == 2 ? launch_umma_gemm<EPI, 2>(tmA, tmB, prm, pp.grid * 2, st)
                     : launch_umma_gemm<EPI, 1>(tmA, tmB, prm, pp.grid, st);
 }

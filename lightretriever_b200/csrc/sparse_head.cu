@@ -186,6 +186,7 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   prm.policy_b = l2_policy(env_int("LR_SPARSE_HEAD_POLICY_B", 0));
   const int clusters = prm.units < geo.n_clusters ? prm.units : geo.n_clusters;
   const int grid = clusters * geo.cl;
+  if (geo.pair) return launch_umma_gemm<EPI_MAXTOK, 2, true>(tmA, tmB, prm, grid, st);
   return geo.cl == 2 ? launch_umma_gemm<EPI_MAXTOK, 2>(tmA, tmB, prm, grid, st)
                      : launch_umma_gemm<EPI_MAXTOK, 1>(tmA, tmB, prm, grid, st);
 }

@@ -34,10 +34,16 @@ namespace lr {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int PIPE_BYTES = 4 * (A_BYTES + B_BYTES);  // shared memory of the operand ring (192 KB)
+// cta_group::1 (single CTA or multicast cluster): a stage holds A (16 KB) + the whole B tile (32 KB): 4 stages.
+// cta_group::2 (CTA pair, one M=256 MMA): a stage holds A (16 KB) + this CTA's HALF of B (16 KB): 6 stages.
+template <bool PAIR> struct PipeCfg {
+  static constexpr int kBBytes = PAIR ? B_BYTES / 2 : B_BYTES;
+  static constexpr int kStageBytes = A_BYTES + kBBytes;
+  static constexpr int kStages = PIPE_BYTES / kStageBytes;
+};
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STAGES = 2;
@@ -45,7 +51,9 @@ constexpr int SMEM_BAR_BYTES = 256;
 constexpr int SMEM_HIST_BYTES = 4 * 256 * 4;
 constexpr int LIST_STAGE_ENTRIES = 768;  // per epilogue warp: a candidate list of <= 768 entries is compacted in smem
 constexpr int SMEM_LIST_BYTES = 4 * LIST_STAGE_ENTRIES * 8;
-constexpr int GEMM_SMEM_TOTAL = 1024 + STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_LIST_BYTES;
+constexpr int SMEM_CS_BYTES = 4 * BN * 4;  // per epilogue warp: the column scales of the current tile
+constexpr int GEMM_SMEM_TOTAL =
+    1024 + PIPE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_LIST_BYTES + SMEM_CS_BYTES;
 static_assert(GEMM_SMEM_TOTAL <= 227 * 1024, "shared memory budget exceeded");
 
 enum { EPI_STORE = 0, EPI_TOPK = 1, EPI_MAXTOK = 2 };
@@ -171,14 +179,20 @@ constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfl
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs own adjacent row tiles of the same column split; each
 // loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, so the L2 -> SM
 // traffic per CTA and k-block drops from 48 KB to 32 KB.  tmB's box then holds BN / CL rows.
-template <int EPI, int CL>
+// PAIR (requires CL == 2): the two CTAs form one cta_group::2 MMA — M = 256 (128 rows per CTA), each CTA stores its A
+// tile and HALF of B (the tensor cores read both halves), the leader CTA's thread issues the MMAs for both, TMA
+// completions of both CTAs are counted on the leader's full barrier, commits are multicast to both CTAs.
+template <int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
+  static_assert(!PAIR || CL == 2, "cta_group::2 needs a cluster of two CTAs");
+  constexpr int STAGES = PipeCfg<PAIR>::kStages;
+  constexpr int STAGE_BYTES = PipeCfg<PAIR>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + PIPE_BYTES;
   // barrier map (8 bytes each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then the TMEM pointer slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -186,10 +200,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
-  uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + SMEM_BAR_BYTES);
-  uint64_t* list_stage_all =
-      reinterpret_cast<uint64_t*>(smem_gen + STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + PIPE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + PIPE_BYTES + SMEM_BAR_BYTES);
+  uint64_t* list_stage_all = reinterpret_cast<uint64_t*>(smem_gen + PIPE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES);
+  float* cs_all = reinterpret_cast<float*>(smem_gen + PIPE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_LIST_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -203,17 +217,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tensormap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);  // every CTA of the cluster must have consumed the slot
+      // multicast cluster: every CTA must have consumed the slot; pair: one multicast commit of the leader
+      mbar_init(empty_bar(s), PAIR ? 1 : CL);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs for a pair)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -236,6 +256,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+            if (PAIR) {
+              // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+              const uint32_t leader_full = mapa_cluster(full_bar(stage), 0);
+              if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+              tma_load_2d_2sm(a_dst, &tmA, kb * BK, m_tile * BM, leader_full, p.policy_a);
+              tma_load_2d_2sm(a_dst + A_BYTES, &tmB, kb * BK, int(cb) + cta_rank * (BN / 2), leader_full, p.policy_b);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+              continue;
+            }
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d_hint(a_dst, &tmA, kb * BK, m_tile * BM, full_bar(stage), p.policy_a);
             if (CL == 1) {
@@ -255,8 +287,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && (!PAIR || cta_rank == 0)) {  // pair: the leader CTA issues for both
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -279,18 +311,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
               // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc,
-                        (kb | kk) != 0 ? 1u : 0u);
+              if (PAIR)
+                umma_bf16_2sm(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc,
+                              (kb | kk) != 0 ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc,
+                          (kb | kk) != 0 ? 1u : 0u);
             }
             // the smem slot is free once these MMAs have read it — in every CTA the multicast writes to
-            if (CL == 1) umma_commit(empty_bar(stage));
+            if (PAIR) umma_commit_2sm_mc(empty_bar(stage), kMcMask);
+            else if (CL == 1) umma_commit(empty_bar(stage));
             else umma_commit_mc(empty_bar(stage), kMcMask);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          // accumulator complete -> epilogue (of both CTAs for a pair)
+          if (PAIR) umma_commit_2sm_mc(tfull_bar(acc), kMcMask);
+          else umma_commit(tfull_bar(acc));
           if (++acc == ACC_STAGES) {
             acc = 0;
             acc_phase ^= 1u;
@@ -304,6 +343,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = quarter * 32 + lane;
     uint32_t* hist = hist_all + (warp - 2) * 256;
     uint64_t* list_stage = list_stage_all + (warp - 2) * LIST_STAGE_ENTRIES;
+    float* cs_smem = cs_all + (warp - 2) * BN;
+    const bool has_scale = (EPI == EPI_TOPK) && (p.q_scale != nullptr || p.c_scale != nullptr);
     const uint32_t full = 0xFFFFFFFFu;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -343,35 +384,58 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           thr = fmaxf(thr_local, tg);
           if (p.debug_flags & 1) thr = INFINITY;
         }
+        if (EPI == EPI_TOPK && has_scale) {
+          // column scales of this tile -> shared memory (read back as broadcasts), overlapped with the MMA wait
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) {
+            const int64_t dcol = cb + i * 32 + lane;
+            cs_smem[i * 32 + lane] = (p.c_scale && dcol < p.cols) ? p.c_scale[dcol] : (p.c_scale ? 0.0f : 1.0f);
+          }
+          __syncwarp();
+        }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (c * 32 >= n_valid) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + uint32_t(c * 32), v);
-          tmem_ld_wait();
-          const int col_lim = n_valid - c * 32;  // columns >= col_lim are padding
-          if (EPI == EPI_STORE) {
-            if (row_valid) {
+        if (EPI == EPI_TOPK) {
+          // Software-pipelined over 32-column chunks: while chunk c is compared against the threshold (pure register
+          // work), the tcgen05.ld of chunk c+1 is in flight.  A chunk first yields a 32-bit pass mask; the (rare) appends
+          // and list cuts run only after the in-flight load has completed.
+          const int nchunks = (n_valid + 31) >> 5;
+          auto pass_mask = [&](const uint32_t (&v)[32], int c) -> uint32_t {
+            uint32_t m = 0;
+            if (has_scale) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < col_lim) p.dbg_scores[row * p.cols + cb + c * 32 + j] = __uint_as_float(v[j]);
-            }
-          } else if (EPI == EPI_TOPK) {
-            float cs_lane = 1.0f;
-            const bool has_cs = p.c_scale != nullptr;
-            if (has_cs) {
-              const int64_t dcol = cb + c * 32 + lane;
-              cs_lane = dcol < p.cols ? p.c_scale[dcol] : 0.0f;
-            }
+                m |= (__uint_as_float(v[j]) * (qs * cs_smem[c * 32 + j]) > thr) ? (1u << j) : 0u;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(v[j]) * qs;
-              if (has_cs) s *= __shfl_sync(full, cs_lane, j);
-              if (s > thr && j < col_lim) {
-                st_cg_u64(buf + cnt, make_key(f32_to_key(s), uint32_t(cb + c * 32 + j)));
+              for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+            }
+            const int lim = n_valid - c * 32;  // columns >= lim are padding
+            return lim >= 32 ? m : (m & ((1u << lim) - 1u));
+          };
+          auto append_and_cut = [&](const uint32_t (&v)[32], uint32_t m, int c) {
+            // Hits are rare once the thresholds are warm: walk only the columns in which ANY lane of the warp has a hit
+            // (warp-uniform j: the switch that picks v[j] does not diverge), instead of 32 divergent per-lane tests.
+            uint32_t u = __reduce_or_sync(full, m);
+            while (u) {
+              const int j = __ffs(u) - 1;
+              u &= u - 1;
+              uint32_t x;
+              switch (j) {
+#define LR_PICK(J) case J: x = v[J]; break;
+                LR_PICK(0) LR_PICK(1) LR_PICK(2) LR_PICK(3) LR_PICK(4) LR_PICK(5) LR_PICK(6) LR_PICK(7)
+                LR_PICK(8) LR_PICK(9) LR_PICK(10) LR_PICK(11) LR_PICK(12) LR_PICK(13) LR_PICK(14) LR_PICK(15)
+                LR_PICK(16) LR_PICK(17) LR_PICK(18) LR_PICK(19) LR_PICK(20) LR_PICK(21) LR_PICK(22) LR_PICK(23)
+                LR_PICK(24) LR_PICK(25) LR_PICK(26) LR_PICK(27) LR_PICK(28) LR_PICK(29) LR_PICK(30)
+                default: x = v[31]; break;
+#undef LR_PICK
+              }
+              if ((m >> j) & 1u) {
+                float sc = __uint_as_float(x);
+                if (has_scale) sc *= (qs * cs_smem[c * 32 + j]);
+                st_cg_u64(buf + cnt, make_key(f32_to_key(sc), uint32_t(cb + c * 32 + j)));
                 ++cnt;
               }
             }
@@ -391,31 +455,68 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 atomicMax(p.gthr + row, vk);  // publish: valid lower bound of this query's global k-th score
               }
             }
-          } else {  // EPI_MAXTOK
-            const int64_t tok = cb + c * 32 + lane;
-            const bool mval = (tok < c1) && (p.mask[tok] != 0);
-            const uint32_t mword = __ballot_sync(full, mval);
+          };
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(t_addr, va);
+#pragma unroll 1
+          for (int c = 0; c < nchunks; c += 2) {
+            const bool has_b = c + 1 < nchunks;
+            tmem_ld_wait();
+            if (has_b) tmem_ld_32x32(t_addr + uint32_t((c + 1) * 32), vb);
+            const uint32_t ma = pass_mask(va, c);
+            if (has_b) tmem_ld_wait();  // vb is architecturally complete before any store / call below
+            append_and_cut(va, ma, c);
+            if (has_b) {
+              const bool has_a2 = c + 2 < nchunks;
+              if (has_a2) tmem_ld_32x32(t_addr + uint32_t((c + 2) * 32), va);
+              const uint32_t mb = pass_mask(vb, c + 1);
+              if (has_a2) tmem_ld_wait();
+              append_and_cut(vb, mb, c + 1);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            if (c * 32 >= n_valid) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(t_addr + uint32_t(c * 32), v);
+            tmem_ld_wait();
+            const int col_lim = n_valid - c * 32;  // columns >= col_lim are padding
+            if (EPI == EPI_STORE) {
+              if (row_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t n = cb + c * 32 + j;
-              if (j < col_lim) {
-                if (n == seg_end) {  // warp-uniform: a document ended right before this token
-                  float x = run_max;
-                  if (p.relu) x = fmaxf(x, 0.0f);
-                  if (p.log1p) x = log1pf(x);
-                  if (row_valid) p.out[seg * p.rows + row] = x;
-                  run_max = BF16_LOWEST;
-                  ++seg;
-                  seg_end += p.seg_len;
+                for (int j = 0; j < 32; ++j)
+                  if (j < col_lim) p.dbg_scores[row * p.cols + cb + c * 32 + j] = __uint_as_float(v[j]);
+              }
+            } else {  // EPI_MAXTOK
+              const int64_t tok = cb + c * 32 + lane;
+              const bool mval = (tok < c1) && (p.mask[tok] != 0);
+              const uint32_t mword = __ballot_sync(full, mval);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t n = cb + c * 32 + j;
+                if (j < col_lim) {
+                  if (n == seg_end) {  // warp-uniform: a document ended right before this token
+                    float x = run_max;
+                    if (p.relu) x = fmaxf(x, 0.0f);
+                    if (p.log1p) x = log1pf(x);
+                    if (row_valid) p.out[seg * p.rows + row] = x;
+                    run_max = BF16_LOWEST;
+                    ++seg;
+                    seg_end += p.seg_len;
+                  }
+                  if ((mword >> j) & 1u) run_max = fmaxf(run_max, __uint_as_float(v[j]) + bias_v);
                 }
-                if ((mword >> j) & 1u) run_max = fmaxf(run_max, __uint_as_float(v[j]) + bias_v);
               }
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));  // leader's barrier
+          else mbar_arrive(tempty_bar(acc));
+        }
         if (++acc == ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1u;
@@ -436,7 +537,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -497,10 +599,10 @@ struct ProfileEvents {
 };
 ProfileEvents& profile_events();  // thread-local, defined in api.cu
 
-template <int EPI, int CL>
+template <int EPI, int CL, bool PAIR = false>
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
-  auto kern = umma_gemm_kernel<EPI, CL>;
+  auto kern = umma_gemm_kernel<EPI, CL, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
@@ -535,13 +637,17 @@ inline uint64_t l2_policy(int code) {
 
 // Work plan shared by the hosts of K2 and K3: groups of CL row tiles, bands of groups, grid of whole clusters.
 struct GemmGeometry {
-  int cl, m_tiles, m_groups, band_size, n_bands, n_clusters;
+  int cl, pair, m_tiles, m_groups, band_size, n_bands, n_clusters;
 };
-inline GemmGeometry plan_geometry(int64_t rows, int band_max_tiles, int force_cl) {
+// mode: 0 = auto, 1 = single CTA, 2 = cluster of 2 with multicast B, 3 = cta_group::2 pair
+inline GemmGeometry plan_geometry(int64_t rows, int band_max_tiles, int mode) {
   GemmGeometry g{};
   g.m_tiles = int((rows + BM - 1) / BM);
   g.cl = (g.m_tiles >= 2) ? 2 : 1;
-  if (force_cl == 1 || force_cl == 2) g.cl = force_cl;
+  g.pair = 0;
+  if (mode == 1) g.cl = 1;
+  if (mode == 2) g.cl = 2;
+  if (mode == 3) { g.cl = 2; g.pair = 1; }
   g.m_groups = (g.m_tiles + g.cl - 1) / g.cl;
   int band_max = band_max_tiles / g.cl;
   plan_bands(g.m_groups, band_max < 1 ? 1 : band_max, g.band_size, g.n_bands);
