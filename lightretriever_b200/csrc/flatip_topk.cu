@@ -135,6 +135,19 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
 template <int EPI>
 static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const GemmParams& prm, cudaStream_t st) {
+  // Long candidate lists (k > 352) in SHORT units: the variant that trades a pipeline stage for a larger list-staging
+  // area.  Measured at k=1000 (profiles/k2_ab_same_box_r1.jsonl): 129 -> 107 ms on the 1.1M-document shard (390 tiles per
+  // unit), but 810 -> 833 ms at 8.8M documents (1427 tiles per unit), where the cuts are amortised and the shallower
+  // operand ring costs more than it saves.
+  const int tiles_per_unit = (pp.tile_end - pp.tile_begin + pp.splits - 1) / pp.splits;
+  const int big_mode = env_int("LR_FLATIP_BIGLIST", -1);
+  const bool big = EPI == EPI_TOPK && pl.cap > LIST_STAGE_ENTRIES &&
+                   (big_mode == 1 || (big_mode == -1 && tiles_per_unit < 1000));
+  if (big) {
+    if (pl.pair) return launch_umma_gemm<EPI_TOPK, 2, true, true>(tmA, tmB, prm, pp.grid * 2, st);
+    return pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2, false, true>(tmA, tmB, prm, pp.grid * 2, st)
+                      : launch_umma_gemm<EPI_TOPK, 1, false, true>(tmA, tmB, prm, pp.grid, st);
+  }
   if (pl.pair) return launch_umma_gemm<EPI, 2, true>(tmA, tmB, prm, pp.grid * 2, st);
   return pl.cl == 2 ? launch_umma_gemm<EPI, 2>(tmA, tmB, prm, pp.grid * 2, st)
                     : launch_umma_gemm<EPI, 1>(tmA, tmB, prm, pp.grid, st);

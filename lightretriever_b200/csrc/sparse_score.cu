@@ -10,9 +10,11 @@
 //   1. every query term looks up its posting sub-range [blockptr[t][b], blockptr[t][b+1]) (no search);
 //   2. the sub-ranges are flattened and all 256 threads stream (doc, impact) pairs with independent,
 //      coalesced loads and atomicAdd count*impact into shared memory;
-//   3. the accumulators are scanned once; entries beating the unit's running threshold (a full 64-bit
-//      (score, ~id) key) are appended to a shared-memory candidate list; when the list would overflow, a
-//      block-wide 64-bit radix select cuts list ∪ block back to the exact top-k and raises the threshold.
+//   3. only the accumulators touched in this block are visited (the first atomicAdd that finds 0 records the
+//      slot in a shared-memory list; > 4096 touches fall back to a full scan); entries beating the unit's running
+//      threshold (a full 64-bit (score, ~id) key) are appended to a shared-memory candidate list; when the list
+//      would overflow, a block-wide 64-bit radix select cuts list ∪ block back to the exact top-k and raises the
+//      threshold.
 // The unit's list goes to the workspace and lr_topk_merge produces the sorted result.
 #include "common.cuh"
 
@@ -21,6 +23,7 @@ namespace lr {
 constexpr int SS_THREADS = 256;
 constexpr int SS_BLOCK_DOCS = 16384;
 constexpr int SS_TERM_CHUNK = 256;
+constexpr int SS_TOUCH_CAP = 4096;  // touched-accumulator list; a block that touches more falls back to a full scan
 
 struct SSParams {
   const int32_t* q_indptr;
@@ -68,12 +71,14 @@ sparse_score_kernel(const SSParams p) {
   int64_t* t_start = reinterpret_cast<int64_t*>(other + p.cap);
   int32_t* t_pre = reinterpret_cast<int32_t*>(t_start + SS_TERM_CHUNK);
   int32_t* t_w = t_pre + SS_TERM_CHUNK;
+  uint16_t* touched = reinterpret_cast<uint16_t*>(t_w + SS_TERM_CHUNK);  // [SS_TOUCH_CAP] accumulators written this block
   __shared__ uint32_t hist[256];
   __shared__ int warp_sums[SS_THREADS / 32];
-  __shared__ uint32_t s_n, s_bin, s_rem, s_take;
+  __shared__ uint32_t s_n, s_nt, s_bin, s_rem, s_take;
   const int tid = threadIdx.x;
 
   for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS) acc[i] = 0;
+  if (tid == 0) s_nt = 0;
   __syncthreads();
 
   const int64_t n_units = p.Q * p.S;
@@ -87,22 +92,51 @@ sparse_score_kernel(const SSParams p) {
     uint32_t n = 0;                    // entries in `list` (uniform copy of s_n between blocks)
     uint64_t thr = 0xFFFFFFFFull;      // candidates need key > thr; every score-0 key is <= this
     if (tid == 0) s_n = 0;
+    // fast path (<= 256 query terms, the normal case): every thread owns one term and walks its block pointers with a
+    // one-block-ahead prefetch, so the term set-up of a block costs no exposed global latency
+    const bool one_chunk = nterms <= SS_TERM_CHUNK;
+    const uint32_t* bp_row = nullptr;
+    int64_t post_base = 0;
+    int my_w = 0;
+    uint32_t lo = 0, hi = 0, nxt = 0;
+    if (one_chunk && tid < nterms) {
+      const int t = p.q_tok[qt0 + tid];
+      if (t >= 0 && t < p.V) {
+        bp_row = p.blockptr + int64_t(t) * (p.nblk + 1);
+        post_base = p.post_indptr[t];
+        my_w = p.q_cnt[qt0 + tid];
+        lo = bp_row[b0];
+        hi = bp_row[b0 + 1];
+        nxt = (b0 + 2 <= p.nblk) ? bp_row[b0 + 2] : hi;
+      }
+    }
     __syncthreads();
 
     for (int b = b0; b < b1; ++b) {
       const int64_t d0 = int64_t(b) * SS_BLOCK_DOCS;
       // ---- 1+2: accumulate the block's postings
       for (int tc = 0; tc < nterms; tc += SS_TERM_CHUNK) {
-        const int i = tc + tid;
         int cnt = 0;
-        if (i < nterms) {
-          const int t = p.q_tok[qt0 + i];
-          if (t >= 0 && t < p.V) {
-            const uint32_t* bp = p.blockptr + int64_t(t) * (p.nblk + 1) + b;
-            const uint32_t lo = bp[0], hi = bp[1];
-            t_start[tid] = p.post_indptr[t] + lo;
+        if (one_chunk) {
+          if (bp_row) {
+            t_start[tid] = post_base + lo;
             cnt = int(hi - lo);
-            t_w[tid] = p.q_cnt[qt0 + i];
+            t_w[tid] = my_w;
+            lo = hi;
+            hi = nxt;
+            if (b + 3 <= p.nblk && b + 1 < b1) nxt = bp_row[b + 3];  // consumed two blocks from now
+          }
+        } else {
+          const int i = tc + tid;
+          if (i < nterms) {
+            const int t = p.q_tok[qt0 + i];
+            if (t >= 0 && t < p.V) {
+              const uint32_t* bp = p.blockptr + int64_t(t) * (p.nblk + 1) + b;
+              const uint32_t l2 = bp[0], h2 = bp[1];
+              t_start[tid] = p.post_indptr[t] + l2;
+              cnt = int(h2 - l2);
+              t_w[tid] = p.q_cnt[qt0 + i];
+            }
           }
         }
         int total;
@@ -112,37 +146,45 @@ sparse_score_kernel(const SSParams p) {
         const int nt = min(SS_TERM_CHUNK, nterms - tc);
         for (int j = tid; j < total; j += SS_THREADS) {
           // largest i in [0, nt) with t_pre[i] <= j
-          int lo = 0, hi = nt - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (t_pre[mid] <= j) lo = mid; else hi = mid - 1;
+          int l = 0, h = nt - 1;
+          while (l < h) {
+            const int mid = (l + h + 1) >> 1;
+            if (t_pre[mid] <= j) l = mid; else h = mid - 1;
           }
-          const int64_t idx = t_start[lo] + (j - t_pre[lo]);
+          const int64_t idx = t_start[l] + (j - t_pre[l]);
           const int doc = p.post_doc[idx];
-          const int imp = int(p.post_imp[idx]);
-          atomicAdd(&acc[doc - d0], t_w[lo] * imp);
+          const int add = t_w[l] * int(p.post_imp[idx]);
+          if (add != 0) {
+            const int slot = doc - int(d0);
+            if (atomicAdd(&acc[slot], add) == 0) {  // first touch of this accumulator in this block
+              const uint32_t tpos = atomicAdd(&s_nt, 1u);
+              if (tpos < SS_TOUCH_CAP) touched[tpos] = uint16_t(slot);
+            }
+          }
         }
         __syncthreads();
       }
-      // ---- 3: scan
+      // ---- 3: visit the touched accumulators (or all of them when the touched list overflowed)
+      const uint32_t nt_all = s_nt;
+      const bool dense = nt_all > SS_TOUCH_CAP;
+      const int n_visit = dense ? SS_BLOCK_DOCS : int(nt_all);
+      auto slot_of = [&](int i) -> int { return dense ? i : int(touched[i]); };
       int c = 0;
-      for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS) {
-        const int sc = acc[i];
-        if (sc > 0 && make_key(uint32_t(sc), uint32_t(d0 + i)) > thr) ++c;
+      for (int i = tid; i < n_visit; i += SS_THREADS) {
+        const int sl = slot_of(i);
+        const int sc = acc[sl];
+        if (sc > 0 && make_key(uint32_t(sc), uint32_t(d0 + sl)) > thr) ++c;
       }
       uint32_t base = c ? atomicAdd(&s_n, uint32_t(c)) : 0u;
       __syncthreads();
       const uint32_t total_n = s_n;
-      if (total_n == n) {
-        // nothing qualified: just clear what was touched
-        for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS)
-          if (acc[i] != 0) acc[i] = 0;
-      } else if (total_n <= uint32_t(p.cap)) {
-        for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS) {
-          const int sc = acc[i];
+      if (total_n <= uint32_t(p.cap)) {
+        for (int i = tid; i < n_visit; i += SS_THREADS) {
+          const int sl = slot_of(i);
+          const int sc = acc[sl];
           if (sc != 0) {
-            acc[i] = 0;
-            const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + i));
+            acc[sl] = 0;
+            const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + sl));
             if (sc > 0 && key > thr) list[base++] = key;
           }
         }
@@ -160,10 +202,11 @@ sparse_score_kernel(const SSParams p) {
             const uint64_t key = list[i];
             if (pass == 7 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
           }
-          for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS) {
-            const int sc = acc[i];
+          for (int i = tid; i < n_visit; i += SS_THREADS) {
+            const int sl = slot_of(i);
+            const int sc = acc[sl];
             if (sc > 0) {
-              const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + i));
+              const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + sl));
               if (key > thr && (pass == 7 || (key >> (shift + 8)) == prefix))
                 atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
             }
@@ -195,11 +238,12 @@ sparse_score_kernel(const SSParams p) {
           const uint64_t key = list[i];
           if (key >= kstar) other[atomicAdd(&s_n, 1u)] = key;
         }
-        for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS) {
-          const int sc = acc[i];
+        for (int i = tid; i < n_visit; i += SS_THREADS) {
+          const int sl = slot_of(i);
+          const int sc = acc[sl];
           if (sc != 0) {
-            acc[i] = 0;
-            const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + i));
+            acc[sl] = 0;
+            const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + sl));
             if (sc > 0 && key > thr && key >= kstar) other[atomicAdd(&s_n, 1u)] = key;
           }
         }
@@ -211,6 +255,8 @@ sparse_score_kernel(const SSParams p) {
         thr = kstar;
       }
       __syncthreads();
+      if (tid == 0) s_nt = 0;
+      // (the next block's first __syncthreads orders this reset before any new touch)
     }
     // ---- unit result
     uint64_t* dst = p.cand + (int64_t(s) * p.Q + q) * p.cap;
@@ -247,7 +293,7 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   pl.nblk = int((N + SS_BLOCK_DOCS - 1) / SS_BLOCK_DOCS);
   int cap = 2 * k > k + 256 ? 2 * k : k + 256;
   pl.cap = (cap + 63) / 64 * 64;
-  pl.smem = size_t(SS_BLOCK_DOCS) * 4 + size_t(pl.cap) * 16 + SS_TERM_CHUNK * (8 + 4 + 4);
+  pl.smem = size_t(SS_BLOCK_DOCS) * 4 + size_t(pl.cap) * 16 + SS_TERM_CHUNK * (8 + 4 + 4) + SS_TOUCH_CAP * 2;
   const int G = sm_count();
   const int ctas_per_sm = int((size_t(227) * 1024) / (pl.smem + 2048));
   const int slots = G * (ctas_per_sm < 1 ? 1 : ctas_per_sm);

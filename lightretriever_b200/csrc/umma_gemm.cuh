@@ -39,10 +39,13 @@ constexpr int B_BYTES = BN * BK * 2;
 constexpr int PIPE_BYTES = 4 * (A_BYTES + B_BYTES);  // shared memory of the operand ring (192 KB)
 // cta_group::1 (single CTA or multicast cluster): a stage holds A (16 KB) + the whole B tile (32 KB): 4 stages.
 // cta_group::2 (CTA pair, one M=256 MMA): a stage holds A (16 KB) + this CTA's HALF of B (16 KB): 6 stages.
-template <bool PAIR> struct PipeCfg {
+// BIGLIST (top-k with long candidate lists, k > 352): one 48 KB stage (two 32 KB stages for a pair) is given to the
+// epilogue warps' list-staging area instead, so that lists of up to 2304 (2816) entries are still cut in shared memory.
+template <bool PAIR, bool BIGLIST> struct PipeCfg {
   static constexpr int kBBytes = PAIR ? B_BYTES / 2 : B_BYTES;
   static constexpr int kStageBytes = A_BYTES + kBBytes;
-  static constexpr int kStages = PIPE_BYTES / kStageBytes;
+  static constexpr int kStages = PIPE_BYTES / kStageBytes - (BIGLIST ? (PAIR ? 2 : 1) : 0);
+  static constexpr int kPipeBytes = kStages * kStageBytes;
 };
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
@@ -51,6 +54,9 @@ constexpr int SMEM_BAR_BYTES = 256;
 constexpr int SMEM_HIST_BYTES = 4 * 256 * 4;
 constexpr int LIST_STAGE_ENTRIES = 768;  // per epilogue warp: a candidate list of <= 768 entries is compacted in smem
 constexpr int SMEM_LIST_BYTES = 4 * LIST_STAGE_ENTRIES * 8;
+template <bool PAIR, bool BIGLIST> struct ListCfg {
+  static constexpr int kEntries = LIST_STAGE_ENTRIES + (PIPE_BYTES - PipeCfg<PAIR, BIGLIST>::kPipeBytes) / (4 * 8);
+};
 constexpr int SMEM_CS_BYTES = 4 * BN * 4;  // per epilogue warp: the column scales of the current tile
 constexpr int GEMM_SMEM_TOTAL =
     1024 + PIPE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_LIST_BYTES + SMEM_CS_BYTES;
@@ -174,6 +180,21 @@ static __device__ __noinline__ uint32_t warp_compact_topk(uint64_t* buf, int n, 
   return vk;
 }
 
+// v[j] for a per-thread dynamic j in [0, 32): 16+8+4+2+1 selects, no branches, no local memory
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+  const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = b3 ? c[2 * i + 1] : c[2 * i];
+  return b4 ? d[1] : d[0];
+}
+
 constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
 
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs own adjacent row tiles of the same column split; each
@@ -182,17 +203,20 @@ constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfl
 // PAIR (requires CL == 2): the two CTAs form one cta_group::2 MMA — M = 256 (128 rows per CTA), each CTA stores its A
 // tile and HALF of B (the tensor cores read both halves), the leader CTA's thread issues the MMAs for both, TMA
 // completions of both CTAs are counted on the leader's full barrier, commits are multicast to both CTAs.
-template <int EPI, int CL, bool PAIR>
+template <int EPI, int CL, bool PAIR, bool BIGLIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   static_assert(!PAIR || CL == 2, "cta_group::2 needs a cluster of two CTAs");
-  constexpr int STAGES = PipeCfg<PAIR>::kStages;
-  constexpr int STAGE_BYTES = PipeCfg<PAIR>::kStageBytes;
+  constexpr int STAGES = PipeCfg<PAIR, BIGLIST>::kStages;
+  constexpr int STAGE_BYTES = PipeCfg<PAIR, BIGLIST>::kStageBytes;
+  constexpr int kPipe = PipeCfg<PAIR, BIGLIST>::kPipeBytes;
+  constexpr int kListEntries = ListCfg<PAIR, BIGLIST>::kEntries;
+  // shared memory map: operand ring | barriers | histograms | column scales | list staging (takes what the ring left)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + PIPE_BYTES;
+  const uint32_t bar_base = smem_base + kPipe;
   // barrier map (8 bytes each): full[STAGES], empty[STAGES], tfull[2], tempty[2], then the TMEM pointer slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -200,10 +224,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + PIPE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
-  uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + PIPE_BYTES + SMEM_BAR_BYTES);
-  uint64_t* list_stage_all = reinterpret_cast<uint64_t*>(smem_gen + PIPE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES);
-  float* cs_all = reinterpret_cast<float*>(smem_gen + PIPE_BYTES + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_LIST_BYTES);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kPipe + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + kPipe + SMEM_BAR_BYTES);
+  float* cs_all = reinterpret_cast<float*>(smem_gen + kPipe + SMEM_BAR_BYTES + SMEM_HIST_BYTES);
+  uint64_t* list_stage_all =
+      reinterpret_cast<uint64_t*>(smem_gen + kPipe + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_CS_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -342,7 +367,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     uint32_t* hist = hist_all + (warp - 2) * 256;
-    uint64_t* list_stage = list_stage_all + (warp - 2) * LIST_STAGE_ENTRIES;
+    uint64_t* list_stage = list_stage_all + (warp - 2) * kListEntries;
     float* cs_smem = cs_all + (warp - 2) * BN;
     const bool has_scale = (EPI == EPI_TOPK) && (p.q_scale != nullptr || p.c_scale != nullptr);
     const uint32_t full = 0xFFFFFFFFu;
@@ -416,28 +441,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             return lim >= 32 ? m : (m & ((1u << lim) - 1u));
           };
           auto append_and_cut = [&](const uint32_t (&v)[32], uint32_t m, int c) {
-            // Hits are rare once the thresholds are warm: walk only the columns in which ANY lane of the warp has a hit
-            // (warp-uniform j: the switch that picks v[j] does not diverge), instead of 32 divergent per-lane tests.
-            uint32_t u = __reduce_or_sync(full, m);
-            while (u) {
-              const int j = __ffs(u) - 1;
-              u &= u - 1;
-              uint32_t x;
-              switch (j) {
-#define LR_PICK(J) case J: x = v[J]; break;
-                LR_PICK(0) LR_PICK(1) LR_PICK(2) LR_PICK(3) LR_PICK(4) LR_PICK(5) LR_PICK(6) LR_PICK(7)
-                LR_PICK(8) LR_PICK(9) LR_PICK(10) LR_PICK(11) LR_PICK(12) LR_PICK(13) LR_PICK(14) LR_PICK(15)
-                LR_PICK(16) LR_PICK(17) LR_PICK(18) LR_PICK(19) LR_PICK(20) LR_PICK(21) LR_PICK(22) LR_PICK(23)
-                LR_PICK(24) LR_PICK(25) LR_PICK(26) LR_PICK(27) LR_PICK(28) LR_PICK(29) LR_PICK(30)
-                default: x = v[31]; break;
-#undef LR_PICK
-              }
-              if ((m >> j) & 1u) {
-                float sc = __uint_as_float(x);
-                if (has_scale) sc *= (qs * cs_smem[c * 32 + j]);
-                st_cg_u64(buf + cnt, make_key(f32_to_key(sc), uint32_t(cb + c * 32 + j)));
-                ++cnt;
-              }
+            // Each lane walks its OWN hits (the loop runs max-over-lanes popc(m) times, usually 0..2) and fetches v[j]
+            // with a branch-free 5-level select tree, since registers cannot be indexed dynamically.
+            while (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1;
+              const uint32_t x = select32(v, j);
+              float sc = __uint_as_float(x);
+              if (has_scale) sc *= (qs * cs_smem[c * 32 + j]);
+              st_cg_u64(buf + cnt, make_key(f32_to_key(sc), uint32_t(cb + c * 32 + j)));
+              ++cnt;
             }
             // keep >= 32 free slots for the next chunk; cut full lists back to their top-k
             uint32_t need = __ballot_sync(full, cnt + 32u > uint32_t(p.cap));
@@ -447,7 +460,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int n_r = __shfl_sync(full, int(cnt), r);
               const int64_t row_r = int64_t(m_tile) * BM + quarter * 32 + r;
               uint64_t* buf_r = p.cand + (int64_t(split) * p.row_pad + row_r) * p.cap;
-              const uint32_t vk = warp_compact_topk(buf_r, n_r, p.k, hist, list_stage, LIST_STAGE_ENTRIES, lane);
+              const uint32_t vk = warp_compact_topk(buf_r, n_r, p.k, hist, list_stage, kListEntries, lane);
               if (lane == r) {
                 cnt = uint32_t(p.k);
                 thr_local = key_to_f32(vk);
@@ -599,10 +612,10 @@ struct ProfileEvents {
 };
 ProfileEvents& profile_events();  // thread-local, defined in api.cu
 
-template <int EPI, int CL, bool PAIR = false>
+template <int EPI, int CL, bool PAIR = false, bool BIGLIST = false>
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
-  auto kern = umma_gemm_kernel<EPI, CL, PAIR>;
+  auto kern = umma_gemm_kernel<EPI, CL, PAIR, BIGLIST>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
