@@ -187,6 +187,20 @@ int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_tok, const in
                          float* out_scores, int64_t* out_ids, uint64_t* out_keys,
                          void* workspace, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Hybrid score fusion of two top-k lists per query (dense + sparse), on device
+ *   replaces fuse_scores_linear / fuse_scores_rrf  retriever/score_fuse_utils.py:48-90, 3-46
+ *            (HybridSearch._fuse_results           retriever/hybrid_search.py:207-232)
+ *   scores0/ids0 [Q,k0], scores1/ids1 [Q,k1]: sorted lists as returned by lr_flatip_topk / lr_sparse_score_topk
+ *   (id -1 = padding).  method 0 = linear: sum_s w_s * (x - min_s) / (max_s - min_s + eps) over the union of ids;
+ *   method 1 = rrf: sum_s 1 / (k_rrf + rank_s).  float64 arithmetic in the reference's operation order.
+ *   out_ids [Q, k0+k1] int64 (-1 padded), out_scores [Q, k0+k1] float64 (-inf padded), sorted by (fused desc, id asc);
+ *   out_counts [Q] int32 (size of the union), may be NULL.   k0 + k1 <= 4096.
+ * ------------------------------------------------------------------------- */
+int lr_fuse_topk(const float* scores0, const int64_t* ids0, int k0, const float* scores1, const int64_t* ids1, int k1,
+                 int64_t Q, int method, double w0, double w1, double eps, double k_rrf,
+                 int64_t* out_ids, double* out_scores, int32_t* out_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,8 @@ PROTOTYPES = {
     "lr_set_profile_events": (_i32, [_vp, _vp]),
     "lr_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i64, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "lr_encode_keys": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "lr_fuse_topk": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _i32, C.c_double, C.c_double, C.c_double, C.c_double,
+                            _vp, _vp, _vp, _vp]),
     "lr_sparse_head_max": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "lr_sparsify_scratch_bytes": (_sz, [_i64, _i64]),
     "lr_sparsify_quantize": (_i32, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _vp]),

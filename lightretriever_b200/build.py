@@ -24,6 +24,7 @@ SOURCES = [
     "topk_merge.cu",
     "sparse_head.cu",
     "sparse_score.cu",
+    "fuse_topk.cu",
 ]
 
 NVCC_FLAGS = [

@@ -2,8 +2,9 @@
 
 Mirrors ``HybridSearch`` (reference retriever/hybrid_search.py:25-403) on top of ``FlatIPSearch`` and
 ``ImpactSearch`` and restates ``fuse_scores_linear`` / ``fuse_scores_rrf`` (retriever/score_fuse_utils.py:48-90, 3-46).
-The fusion runs on the host over the two top-k dictionaries exactly like the reference (float64 numpy); it is listed
-as the next row to move on device.
+``fuse_scores_linear`` / ``fuse_scores_rrf`` keep the reference's dict-in / dict-out form (float64 numpy on the host);
+``fuse_topk_device`` is the same arithmetic on device over the sorted (scores, ids) arrays the searchers produce
+(csrc/fuse_topk.cu), bit-exact with the host form and without the 2*Q*k Python dict operations.
 """
 from __future__ import annotations
 
@@ -49,6 +50,42 @@ def fuse_scores_linear(results_list: Sequence[dict], weights: Sequence[float] = 
                 pid = str(pid)
                 fq[pid] = fq.get(pid, 0.0) + float(s)
     return fused
+
+
+def fuse_topk_device(scores0, ids0, scores1, ids1, method: str = "linear", weights: Sequence[float] = (0.7, 0.3),
+                     eps: float = 1e-8, k_rrf: float = 60.0):
+    """Device fusion of two per-query top-k lists (arrays straight from ``flatip_topk`` / ``ImpactIndex.search_device``).
+
+    Same arithmetic as ``fuse_scores_linear`` / ``fuse_scores_rrf`` (float64, reference operation order) without the
+    2*Q*k Python dict operations.  Returns (ids int64 [Q, k0+k1] with -1 padding, fused float64 [Q, k0+k1], counts int32 [Q]),
+    rows sorted by (fused score desc, id asc).
+    """
+    import torch
+
+    from . import _C
+    from ._util import require_cuda, stream_ptr
+
+    s0 = require_cuda(scores0, "scores0").to(torch.float32).contiguous()
+    s1 = require_cuda(scores1, "scores1").to(torch.float32).contiguous()
+    i0 = require_cuda(ids0, "ids0").to(torch.int64).contiguous()
+    i1 = require_cuda(ids1, "ids1").to(torch.int64).contiguous()
+    if s0.shape != i0.shape or s1.shape != i1.shape or s0.shape[0] != s1.shape[0] or s0.ndim != 2 or s1.ndim != 2:
+        raise ValueError("expected scores/ids of shape [Q, k0] and [Q, k1]")
+    if method not in ("linear", "rrf"):
+        raise NotImplementedError(f"score_fuse_method {method} is not supported.")
+    Q, k0 = s0.shape
+    k1 = s1.shape[1]
+    dev = s0.device
+    out_ids = torch.empty((Q, k0 + k1), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((Q, k0 + k1), dtype=torch.float64, device=dev)
+    counts = torch.empty(Q, dtype=torch.int32, device=dev)
+    lib = _C.load()
+    with torch.cuda.device(dev):
+        _C.check(lib.lr_fuse_topk(s0.data_ptr(), i0.data_ptr(), k0, s1.data_ptr(), i1.data_ptr(), k1, Q,
+                                  0 if method == "linear" else 1, float(weights[0]), float(weights[1]), float(eps),
+                                  float(k_rrf), out_ids.data_ptr(), out_scores.data_ptr(), counts.data_ptr(),
+                                  stream_ptr(dev)))
+    return out_ids, out_scores, counts
 
 
 class HybridSearch:

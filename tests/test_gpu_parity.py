@@ -366,6 +366,76 @@ def test_sparse_head_to_sparse_search_roundtrip():
         assert ra.get(qid, {}) == {f"d{j}": float(s) for s, j in zip(es[r], ei[r]) if j >= 0}
 
 
+# ------------------------------------------------------------------------------------------------ fusion + hybrid orchestration
+@pytest.mark.parametrize("k0,k1,method", [(10, 10, "linear"), (100, 37, "linear"), (1000, 1000, "linear"), (64, 100, "rrf")])
+def test_device_fusion_bit_exact_vs_reference_semantics(k0, k1, method):
+    rng = np.random.default_rng(k0 + k1)
+    Q = 9
+    s0 = -np.sort(-rng.standard_normal((Q, k0)).astype(np.float32), axis=1)
+    s1 = -np.sort(-rng.integers(1, 5000, (Q, k1)).astype(np.float32), axis=1)
+    i0 = np.stack([rng.permutation(3 * (k0 + k1))[:k0] for _ in range(Q)]).astype(np.int64)
+    i1 = np.stack([rng.permutation(3 * (k0 + k1))[:k1] for _ in range(Q)]).astype(np.int64)
+    i1[:, : min(k0, k1) // 2] = i0[:, : min(k0, k1) // 2]  # documents returned by both systems
+    i1[0, -3:] = -1  # padding (fewer than k hits)
+    s1[0, -3:] = -np.inf
+    ids, fused, counts = lr.fuse_topk_device(torch.from_numpy(s0).cuda(), torch.from_numpy(i0).cuda(),
+                                             torch.from_numpy(s1).cuda(), torch.from_numpy(i1).cuda(), method=method)
+    ids, fused, counts = _np(ids), fused.cpu().numpy(), _np(counts)
+    for q in range(Q):
+        d0 = {str(i): float(s) for s, i in zip(s0[q], i0[q]) if i >= 0}
+        d1 = {str(i): float(s) for s, i in zip(s1[q], i1[q]) if i >= 0}
+        ref = (oracle.fuse_linear([{"q": d0}, {"q": d1}], weights=[0.7, 0.3]) if method == "linear"
+               else oracle.fuse_rrf([{"q": d0}, {"q": d1}]))["q"]
+        n = counts[q]
+        assert n == len(ref)
+        got = {str(i): f for i, f in zip(ids[q, :n], fused[q, :n])}
+        assert got.keys() == ref.keys()
+        for pid, v in ref.items():
+            assert got[pid] == v, (pid, got[pid], v)  # float64, same operation order -> bit-exact
+        assert (np.diff(fused[q, :n]) <= 0).all() and (ids[q, n:] == -1).all()
+
+
+def test_hybrid_search_end_to_end_with_fake_model():
+    """HybridSearch.search (hybrid_search.py:234-403): chunked dense index/retrieve + heap merge, sparse index per
+    chunk + one retrieve, linear fusion — against the same flow played by the oracle."""
+    gen = torch.Generator().manual_seed(21)
+    n_docs, n_q, d, V, k = 300, 6, 64, 97, 20
+    doc_vec = F.normalize(torch.randn(n_docs, d, generator=gen), dim=-1)
+    q_vec = F.normalize(torch.randn(n_q, d, generator=gen), dim=-1)
+    rng = np.random.default_rng(5)
+    doc_sparse = [{str(int(t)): int(rng.integers(1, 300)) for t in rng.choice(V, 12, replace=False)} for _ in range(n_docs)]
+    q_tok = [" ".join(str(int(t)) for t in rng.integers(0, V, size=6)) for _ in range(n_q)]
+    corpus = {f"d{j}": {"text": "x" * (1 + j % 7), "j": j} for j in range(n_docs)}
+    queries = {f"q{j}": f"query {j}" for j in range(n_q)}
+
+    class FakeModel:
+        def encode_queries(self, queries, **kw):
+            return {"emb_reps": q_vec, "token_id_reps": q_tok}
+
+        def encode_corpus(self, corpus, **kw):
+            idx = [c["j"] for c in corpus]
+            return {"dense_reps": doc_vec[idx], "sparse_reps": [doc_sparse[j] for j in idx]}
+
+    hs = lr.HybridSearch(FakeModel(), batch_size=16, corpus_chunk_size=128, return_all_results=True, vocab_size=V)
+    res = hs.search(corpus, queries, top_k=k)
+    # oracle flow
+    qb, cb = q_vec.bfloat16().float(), doc_vec.bfloat16().float()
+    es, ei = oracle.flatip_topk(qb, cb, k)
+    emb = {f"q{r}": {f"d{j}": float(s) for s, j in zip(es[r], ei[r])} for r in range(n_q)}
+    ts, ti = oracle.impact_topk([oracle.query_counts([int(t) for t in s.split()]) for s in q_tok],
+                                [{int(a): b for a, b in dd.items()} for dd in doc_sparse], k)
+    tok = {f"q{r}": {f"d{j}": float(s) for s, j in zip(ts[r], ti[r]) if j >= 0} for r in range(n_q)}
+    for r in range(n_q):
+        qid = f"q{r}"
+        assert res["emb"][qid].keys() == emb[qid].keys()
+        assert res["tok"].get(qid, {}) == tok.get(qid, {})
+    fused = oracle.fuse_linear([res["emb"], res["tok"]], weights=[0.7, 0.3])
+    for qid in fused:
+        assert res["emb_tok"][qid].keys() == fused[qid].keys()
+        for pid, v in fused[qid].items():
+            assert abs(res["emb_tok"][qid][pid] - v) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_width_properties_at_scale():
     """Size-independent properties at a BASELINE-like width (d=4096) and a corpus larger than L2:
