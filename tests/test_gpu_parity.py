@@ -373,9 +373,11 @@ def test_device_fusion_bit_exact_vs_reference_semantics(k0, k1, method):
     Q = 9
     s0 = -np.sort(-rng.standard_normal((Q, k0)).astype(np.float32), axis=1)
     s1 = -np.sort(-rng.integers(1, 5000, (Q, k1)).astype(np.float32), axis=1)
-    i0 = np.stack([rng.permutation(3 * (k0 + k1))[:k0] for _ in range(Q)]).astype(np.int64)
-    i1 = np.stack([rng.permutation(3 * (k0 + k1))[:k1] for _ in range(Q)]).astype(np.int64)
-    i1[:, : min(k0, k1) // 2] = i0[:, : min(k0, k1) // 2]  # documents returned by both systems
+    h = min(k0, k1) // 2  # documents returned by both systems
+    uni = np.stack([rng.permutation(3 * (k0 + k1)) for _ in range(Q)]).astype(np.int64)
+    i0 = uni[:, :k0].copy()
+    i1 = np.concatenate([i0[:, :h], uni[:, k0:k0 + k1 - h]], axis=1)
+    i1 = np.stack([rng.permutation(row) for row in i1])  # ids are unique inside a system, shared across systems
     i1[0, -3:] = -1  # padding (fewer than k hits)
     s1[0, -3:] = -np.inf
     ids, fused, counts = lr.fuse_topk_device(torch.from_numpy(s0).cuda(), torch.from_numpy(i0).cuda(),
