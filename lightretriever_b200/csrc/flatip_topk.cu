@@ -83,6 +83,7 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   // shard shape (profiles/k2_schedule_sweeps_r1.md): a 32768-document prefix brings the main pass within 2% of a run
   // with perfect thresholds; 4k..8k-document prefixes do not pay for themselves.
   int prefix_tiles = 0;
+  int prefix_splits_forced = 0;
   const int want = env_int("LR_FLATIP_PREFIX_DOCS", -1);
   if (want != 0) {
     int64_t docs = want > 0 ? want : 32768;
@@ -90,8 +91,20 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
     const int pt = int((docs + BN - 1) / BN);
     const bool big_enough = want > 0 || (pl.m_groups >= 4 && pl.n_tiles >= 32 * pt);
     if (big_enough && pt < pl.n_tiles) prefix_tiles = pt;
+    // Small query batches (online serving, HBM-bound): a prefix of one tile per cluster, every cluster scoring a
+    // different tile, costs one tile time and removes the cold-start cuts, which otherwise pile up in the one or two
+    // epilogue warps that own the few valid query rows.
+    if (want < 0 && pl.m_groups < 4 && Q >= 4) {  // a single query cuts its list in ~20k cycles: not worth a pass
+      const int s0 = geo.n_clusters / pl.m_groups;
+      if (s0 >= 8 && pl.n_tiles >= 8 * s0 && 4 * int64_t(k) <= int64_t(s0) * BN) {
+        prefix_tiles = s0;
+        prefix_splits_forced = s0;
+        if (pl.cap < BN + 64) pl.cap = BN + 64;  // a one-tile unit never has to cut its list
+      }
+    }
   }
-  if (prefix_tiles > 0) pl.prefix = plan_pass(pl.m_groups, geo.n_clusters, 0, prefix_tiles, s_cap, 0);
+  if (prefix_tiles > 0)
+    pl.prefix = plan_pass(pl.m_groups, geo.n_clusters, 0, prefix_tiles, s_cap, prefix_splits_forced);
   pl.main = plan_pass(pl.m_groups, geo.n_clusters, prefix_tiles, pl.n_tiles, s_cap, env_int("LR_FLATIP_SPLITS", 0));
 
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
