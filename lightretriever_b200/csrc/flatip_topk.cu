@@ -143,6 +143,7 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
   prm.policy_a = l2_policy(env_int("LR_FLATIP_POLICY_A", 0));
   prm.policy_b = l2_policy(env_int("LR_FLATIP_POLICY_B", 0));
   prm.debug_flags = env_int("LR_FLATIP_DEBUG", 0);
+  prm.k_rot = env_int("LR_FLATIP_KROT", 0);
 }
 
 template <int EPI>

@@ -71,6 +71,7 @@ struct GemmParams {
   int m_groups;                                    // ceil(m_tiles / CL): one group per cluster
   uint64_t policy_a, policy_b;                     // L2 eviction policy of the A (row) and B (column) tile loads
   int debug_flags;                                 // bit 0: epilogue drops every score (main-loop-only timing)
+  int k_rot;                                       // K-block rotation stride per cluster (0 = none), see producer
   // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
   int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range of [tile_begin, n_tiles)
   int tile_begin;
@@ -277,8 +278,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         decode_unit(p, u, m_group, split);
         const int m_tile = m_group * CL + cta_rank;  // may be a padding tile (>= m_tiles): TMA zero-fills it
         split_cols<EPI>(p, split, c0, c1);
+        // Clusters that share a B tile (same split) or an A tile (same row group) run in lock step; starting each
+        // cluster at a different K block keeps them from requesting the same lines at the same moment (all missing in
+        // L2 together) — the first toucher misses, the others hit later.  The sum over K is order-independent.
+        const int rot = p.k_rot ? int((unsigned(cluster_id) * unsigned(p.k_rot)) % unsigned(p.kblocks)) : 0;
         for (int64_t cb = c0; cb < c1; cb += BN) {
-          for (int kb = 0; kb < p.kblocks; ++kb) {
+          for (int kbi = 0; kbi < p.kblocks; ++kbi) {
+            int kb = kbi + rot;
+            if (kb >= p.kblocks) kb -= p.kblocks;
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             if (PAIR) {
