@@ -62,6 +62,19 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic(args, world):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this exact config."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
+            t = json.load(f)
+        c = t["config"]
+        if (c["docs"], c["queries"], c["dim"], c["k"], c["n_gpus"]) == (args.docs, args.queries, args.dim, args.topk, world):
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def make_queries(n_queries: int, seed: int):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -330,7 +343,8 @@ def run_b200(args):
             "roofline": {"kernel": "umma_gemm_kernel<EPI_TOPK> (tcgen05 bf16 GEMM + fused top-k epilogue)",
                          "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
-                         "flop_per_launch": flops, "kernel_ms": kern_ms_mean, "traffic": None,
+                         "flop_per_launch": flops, "kernel_ms": kern_ms_mean, "traffic": load_traffic(args, world),
+                         "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/k2_traffic.json)",
                          "kernel_share_of_step": kern_ms_mean / (total_ms / args.steps)},
             "plan": dict(zip(["m_tiles", "n_tiles", "splits", "band", "cap", "grid", "units", "prefix_tiles"], list(plan))),
             "parity_spot_check": {"queries": nchk, "ids_identical_to_torch_fp32_topk": ids_same, "max_abs_score_err": score_err},
