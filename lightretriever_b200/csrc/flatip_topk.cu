@@ -63,11 +63,6 @@ static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile
 
 static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   FlatipPlan pl{};
-  const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), env_int("LR_FLATIP_CLUSTER", 0));
-  pl.cl = geo.cl; pl.pair = geo.pair; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
-  pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;
-  pl.n_tiles = int((N + BN - 1) / BN);
-  pl.q_pad = int64_t(pl.m_tiles) * BM;
   // Candidate-list capacity.  The running threshold of a row only rises when its list is cut back to the top-k, so
   // between two cuts exactly cap-k entries are admitted and the number of documents consumed grows by cap/k per cut;
   // measured on B200 (profiles/): 2k..2.5k beats both smaller and larger lists.
@@ -76,6 +71,18 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   cap = env_int("LR_FLATIP_CAP", cap);
   if (cap < k + 64) cap = k + 64;
   pl.cap = (cap + 63) / 64 * 64;
+  // Kernel variant.  Default: cluster of 2 with multicast B (the most energy-efficient under the power cap).  Long lists
+  // (k > 352: a list no longer fits the 6 KB/warp staging area) run as a cta_group::2 pair with the BIGLIST layout
+  // (4 stages of 32 KB + 22 KB/warp of list staging): there the epilogue, not power, is the limiter — measured at
+  // k=1000, 8.8M docs: 841 ms (multicast) -> 660 ms (pair + BIGLIST + 256k-document prefix).
+  int mode = env_int("LR_FLATIP_CLUSTER", 0);
+  const bool long_lists = pl.cap > LIST_STAGE_ENTRIES;
+  if (mode == 0 && long_lists && Q > BM) mode = 3;
+  const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), mode);
+  pl.cl = geo.cl; pl.pair = geo.pair; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
+  pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;
+  pl.n_tiles = int((N + BN - 1) / BN);
+  pl.q_pad = int64_t(pl.m_tiles) * BM;
   const int64_t list_bytes = pl.q_pad * int64_t(pl.cap) * 8;
   const int64_t s_cap = (int64_t(12) << 30) / (list_bytes > 0 ? list_bytes : 1);
 
@@ -86,10 +93,12 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   int prefix_splits_forced = 0;
   const int want = env_int("LR_FLATIP_PREFIX_DOCS", -1);
   if (want != 0) {
-    int64_t docs = want > 0 ? want : 32768;
+    // default prefix: 256 documents per requested result, at least 32768, at most 1/16 of the corpus
+    int64_t docs = want > 0 ? want : (int64_t(256) * k > 32768 ? int64_t(256) * k : 32768);
     if (docs < 4 * int64_t(k)) docs = 4 * int64_t(k);
-    const int pt = int((docs + BN - 1) / BN);
-    const bool big_enough = want > 0 || (pl.m_groups >= 4 && pl.n_tiles >= 32 * pt);
+    int pt = int((docs + BN - 1) / BN);
+    if (want < 0 && pt > pl.n_tiles / 16) pt = pl.n_tiles / 16;
+    const bool big_enough = want > 0 || (pl.m_groups >= 4 && pt >= 128 && pl.n_tiles >= 32 * 128);
     if (big_enough && pt < pl.n_tiles) prefix_tiles = pt;
     // Small query batches (online serving, HBM-bound): a prefix of one tile per cluster, every cluster scoring a
     // different tile, costs one tile time and removes the cold-start cuts, which otherwise pile up in the one or two
@@ -149,14 +158,13 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
 template <int EPI>
 static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const GemmParams& prm, cudaStream_t st) {
-  // Long candidate lists (k > 352) in SHORT units: the variant that trades a pipeline stage for a larger list-staging
-  // area.  Measured at k=1000 (profiles/k2_ab_same_box_r1.jsonl): 129 -> 107 ms on the 1.1M-document shard (390 tiles per
-  // unit), but 810 -> 833 ms at 8.8M documents (1427 tiles per unit), where the cuts are amortised and the shallower
-  // operand ring costs more than it saves.
+  // Long candidate lists (k > 352): the BIGLIST layout gives the epilogue warps a larger list-staging area.  For a pair
+  // it is free (4 of 6 stages of 32 KB keep the prefetch depth); for the multicast cluster it costs one of four 48 KB
+  // stages, which only pays in short units (k=1000: 129 -> 107 ms at 390 tiles per unit, 810 -> 833 ms at 1427).
   const int tiles_per_unit = (pp.tile_end - pp.tile_begin + pp.splits - 1) / pp.splits;
   const int big_mode = env_int("LR_FLATIP_BIGLIST", -1);
   const bool big = EPI == EPI_TOPK && pl.cap > LIST_STAGE_ENTRIES &&
-                   (big_mode == 1 || (big_mode == -1 && tiles_per_unit < 1000));
+                   (big_mode == 1 || (big_mode == -1 && (pl.pair || tiles_per_unit < 1000)));
   if (big) {
     if (pl.pair) return launch_umma_gemm<EPI_TOPK, 2, true, true>(tmA, tmB, prm, pp.grid * 2, st);
     return pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2, false, true>(tmA, tmB, prm, pp.grid * 2, st)
