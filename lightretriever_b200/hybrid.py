@@ -162,6 +162,15 @@ class HybridSearch:
                 results["default"] = results["emb_tok"]
         return results
 
+    def retrieve_arrays(self, query_emb: dict, top_k: int):
+        """emb + tok retrieval and fusion without leaving the device: (fused ids i64 [Q, 2k] as corpus positions, fused
+        scores f64 [Q, 2k], counts i32 [Q]).  Both searchers must index the same corpus in the same order."""
+        s0, i0 = self.dense_search.retrieve_arrays(query_emb["emb_reps"] if query_emb.get("emb_reps") is not None
+                                                   else query_emb["dense_reps"], top_k)
+        s1, i1 = self.sparse_search.retrieve_arrays(query_emb["token_id_reps"] if query_emb.get("token_id_reps") is not None
+                                                    else query_emb["sparse_reps"], top_k)
+        return fuse_topk_device(s0, i0, s1, i1, method=self.score_fuse_method, weights=self.fuse_weights)
+
     def _add_to_heap(self, sub_results, result_heaps, top_k, ignore_identical_ids):
         return add_to_heap(sub_results, result_heaps, top_k, ignore_identical_ids)
 

@@ -304,6 +304,27 @@ class FlatIPSearch:
             results[query_ids[i]] = row
         return results
 
+    def retrieve_arrays(self, query_emb, top_k: int, **kwargs):
+        """Device arrays (scores f32 [Q,k], doc positions i64 [Q,k], -1 padded): the f2 row — results stay on device and
+        are turned into the reference's nested dicts only when a caller asks for them (`arrays_to_dict`)."""
+        if self.faiss_index is None:
+            raise RuntimeError("index() must be called before retrieve_arrays()")
+        return self.faiss_index.search_device(query_emb, top_k, **kwargs)
+
+    def arrays_to_dict(self, scores, ids, query_ids: Sequence[str]) -> dict:
+        s, i = scores.cpu().numpy(), ids.cpu().numpy()
+        pid = self.faiss_index._passage_ids
+        out = {}
+        for r, qid in enumerate(query_ids):
+            row = {}
+            for doc, sc in zip(i[r].tolist(), s[r].tolist()):
+                if doc < 0:
+                    continue
+                doc = int(pid[doc - self.faiss_index.id_offset]) if pid is not None else doc
+                row[self.rev_mapping[doc] if self.rev_mapping else str(doc)] = float(sc)
+            out[qid] = row
+        return out
+
     def save(self, output_dir: str, prefix: str = "my-index", ext: str = "flat"):
         save_dict_to_tsv(self.mapping, os.path.join(output_dir, f"{prefix}.{ext}.tsv"), keys=self.mapping_tsv_keys)
         self.faiss_index.save(os.path.join(output_dir, f"{prefix}.{ext}.lrb200"))

@@ -197,6 +197,66 @@ class ImpactSearch:
         self.n_dumped += len(corpus_ids)
         self._index = None
 
+    # ---- on-disk compatibility with the reference's dump (anserini_search.py:89-111): JsonVectorCollection lines
+    #      {"id": ..., "content": "", "vector": {token: int}} in corpusNNNNN.jsonl files of 2000 documents
+    def dump_jsonl(self, folder: str, chunk_docs: int = 2000) -> None:
+        """Write the pending corpus in the reference's JSONL layout (what IndexCollection would ingest)."""
+        import json
+        import os
+
+        os.makedirs(folder, exist_ok=True)
+        n = 0
+        f = None
+        for (indptr, tok, imp), ids in self._pending_with_ids():
+            ip = torch.as_tensor(indptr).tolist()
+            tk = torch.as_tensor(tok).tolist()
+            im = torch.as_tensor(imp).cpu()
+            im = ((im.to(torch.int32) & 0xFFFF) if im.dtype == torch.int16 else im).tolist()
+            for j, cid in enumerate(ids):
+                if n % chunk_docs == 0:
+                    if f:
+                        f.close()
+                    f = open(os.path.join(folder, f"corpus{n // chunk_docs:05d}.jsonl"), "w")
+                vec = {str(tk[i]): int(im[i]) for i in range(ip[j], ip[j + 1])} or {"-1": 1}
+                f.write(json.dumps({"id": cid, "content": "", "vector": vec}) + "\n")
+                n += 1
+        if f:
+            f.close()
+
+    def index_from_jsonl(self, folder: str) -> int:
+        """Ingest a corpus dumped by the reference's AnseriniSearch.index (encoded_corpus/corpusNNNNN.jsonl)."""
+        import glob
+        import json
+        import os
+
+        n = 0
+        for path in sorted(glob.glob(os.path.join(folder, "corpus*.jsonl"))):
+            ids, vecs = [], []
+            with open(path) as f:
+                for line in f:
+                    if not line.strip():
+                        continue
+                    rec = json.loads(line)
+                    ids.append(rec["id"])
+                    vecs.append(rec.get("vector") or {})
+            if ids:
+                self.index(vecs, ids)
+                n += len(ids)
+        return n
+
+    def _pending_with_ids(self):
+        pos = 0
+        for csr in self._pending:
+            n_docs = len(csr[0]) - 1
+            yield csr, self._corpus_ids[pos:pos + n_docs]
+            pos += n_docs
+
+    def retrieve_arrays(self, query_emb: Sequence, top_k: int):
+        """Device arrays (scores f32 [Q,k], doc positions i64 [Q,k], -1 padded) — no dict materialisation."""
+        idx = self._ensure_index()
+        qi, qt, qc = parse_queries(query_emb, idx.V)
+        return idx.search_device(qi, qt, qc, min(int(top_k), 1024))
+
     def _ensure_index(self) -> ImpactIndex:
         if self._index is None:
             if not self._pending:

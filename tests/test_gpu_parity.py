@@ -438,6 +438,40 @@ def test_hybrid_search_end_to_end_with_fake_model():
             assert abs(res["emb_tok"][qid][pid] - v) < 1e-12
 
 
+def test_array_first_retrieval_and_jsonl_roundtrip(tmp_path):
+    """Rows f2 / f3: results stay on device as arrays (dicts only on request), and a corpus dumped in the reference's
+    Anserini JSONL layout (anserini_search.py:89-111) is ingested back with identical search results."""
+    gen = torch.Generator().manual_seed(33)
+    n_docs, n_q, d, V, k = 500, 7, 64, 211, 16
+    doc_vec = F.normalize(torch.randn(n_docs, d, generator=gen), dim=-1)
+    q_vec = F.normalize(torch.randn(n_q, d, generator=gen), dim=-1)
+    rng = np.random.default_rng(9)
+    docs = [{str(int(t)): int(rng.integers(1, 300)) for t in rng.choice(V, 9, replace=False)} for _ in range(n_docs)]
+    docs[17] = {"-1": 1}  # the reference's empty-document marker
+    q_tok = [" ".join(str(int(t)) for t in rng.integers(0, V, size=5)) for _ in range(n_q)]
+    cids = [f"d{j}" for j in range(n_docs)]
+    qids = [f"q{j}" for j in range(n_q)]
+    hs = lr.HybridSearch(model=None, vocab_size=V)
+    hs.index({"dense_reps": doc_vec, "sparse_reps": docs}, cids)
+    fid, fsc, cnt = hs.retrieve_arrays({"emb_reps": q_vec, "token_id_reps": q_tok}, k)
+    dict_res = hs.retrieve_with_emb({"emb_reps": q_vec, "token_id_reps": q_tok}, qids, k)
+    for r, qid in enumerate(qids):
+        n = int(cnt[r])
+        got = {f"d{int(i)}": float(s) for i, s in zip(fid[r, :n].tolist(), fsc[r, :n].tolist())}
+        ref = dict_res["emb_tok"][qid]
+        assert got.keys() == ref.keys()
+        for pid, v in ref.items():
+            assert abs(got[pid] - v) < 1e-12
+    s_arr, i_arr = hs.dense_search.retrieve_arrays(q_vec, k)
+    assert hs.dense_search.arrays_to_dict(s_arr, i_arr, qids) == dict_res["emb"]
+    # JSONL round trip of the sparse corpus
+    hs.sparse_search.dump_jsonl(str(tmp_path / "encoded_corpus"), chunk_docs=128)
+    assert len(list((tmp_path / "encoded_corpus").glob("corpus*.jsonl"))) == 4
+    other = lr.ImpactSearch(vocab_size=V)
+    assert other.index_from_jsonl(str(tmp_path / "encoded_corpus")) == n_docs
+    assert other.retrieve_with_emb(q_tok, qids, k) == dict_res["tok"]
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_width_properties_at_scale():
     """Size-independent properties at a BASELINE-like width (d=4096) and a corpus larger than L2:
