@@ -152,12 +152,20 @@ sparse_score_kernel(const SSParams p) {
             if (t_pre[mid] <= j) l = mid; else h = mid - 1;
           }
           const int64_t idx = t_start[l] + (j - t_pre[l]);
-          const int doc = p.post_doc[idx];
-          const int add = t_w[l] * int(p.post_imp[idx]);
-          if (add != 0) {
-            const int slot = doc - int(d0);
-            if (atomicAdd(&acc[slot], add) == 0) {  // first touch of this accumulator in this block
-              const uint32_t tpos = atomicAdd(&s_nt, 1u);
+          const int doc = __ldg(p.post_doc + idx);
+          const int add = t_w[l] * int(__ldg(p.post_imp + idx));
+          const int slot = doc - int(d0);
+          // first touch of this accumulator in this block -> remember the slot (one shared-counter atomic per warp)
+          const bool first = add != 0 && atomicAdd(&acc[slot], add) == 0;
+          const unsigned am = __activemask();
+          const unsigned fm = __ballot_sync(am, first);
+          if (fm) {
+            const int leader = __ffs(fm) - 1;
+            uint32_t tbase = 0;
+            if ((tid & 31) == leader) tbase = atomicAdd(&s_nt, uint32_t(__popc(fm)));
+            tbase = __shfl_sync(am, tbase, leader);
+            if (first) {
+              const uint32_t tpos = tbase + __popc(fm & ((1u << (tid & 31)) - 1u));
               if (tpos < SS_TOUCH_CAP) touched[tpos] = uint16_t(slot);
             }
           }
