@@ -116,6 +116,13 @@ int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, int64_t ldc
  * (tcgen05) kernel launch, so the caller can read that kernel's device time without a profiler.  NULL, NULL disables. */
 int lr_set_profile_events(void* ev_begin, void* ev_end);
 
+/* Plan of a (Q, N, k) search without running it (needs no CUDA device; 148 SMs are assumed when none is present):
+ * out[0]=CTAs per cluster out[1]=cta_group::2 pair (0|1) out[2]=query tiles out[3]=corpus tiles out[4]=list capacity
+ * out[5]=prefix tiles (0 = single phase) out[6]=prefix splits out[7]=prefix units out[8]=main first tile
+ * out[9]=main splits out[10]=main units out[11]=main grid (CTAs) out[12]=band (query tiles) out[13]=workspace bytes
+ * out[14]=main rounds out[15]=concurrent clusters */
+int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16);
+
 /* Plan of the last lr_flatip_topk call on this thread (for bench / DESIGN):
  * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=rounds */
 int lr_flatip_last_plan(int64_t* out8);

@@ -199,6 +199,21 @@ extern "C" size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k) {
   return make_plan(Q, N, k).total_bytes;
 }
 
+// Plan of a (Q, N, k) search without running it (no device needed beyond the SM count): for tests and capacity planning.
+// out[0]=cluster size (1|2) out[1]=pair (0|1) out[2]=m_tiles out[3]=n_tiles out[4]=cap out[5]=prefix tile_end
+// out[6]=prefix splits out[7]=prefix units out[8]=main tile_begin out[9]=main splits out[10]=main units
+// out[11]=main grid (CTAs) out[12]=band (row tiles) out[13]=workspace bytes out[14]=main rounds out[15]=n_clusters
+extern "C" int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16) {
+  LR_CHECK_ARG(out16 && Q >= 1 && N >= 1 && k >= 1 && k <= 2048, "flatip_plan: bad arguments");
+  const FlatipPlan pl = make_plan(Q, N, k);
+  out16[0] = pl.cl; out16[1] = pl.pair; out16[2] = pl.m_tiles; out16[3] = pl.n_tiles; out16[4] = pl.cap;
+  out16[5] = pl.prefix.tile_end; out16[6] = pl.prefix.splits; out16[7] = pl.prefix.units;
+  out16[8] = pl.main.tile_begin; out16[9] = pl.main.splits; out16[10] = pl.main.units;
+  out16[11] = int64_t(pl.main.grid) * pl.cl; out16[12] = int64_t(pl.band_size) * pl.cl;
+  out16[13] = int64_t(pl.total_bytes); out16[14] = pl.main.rounds; out16[15] = pl.n_clusters;
+  return LR_OK;
+}
+
 extern "C" int lr_flatip_last_plan(int64_t* out8) {
   const FlatipPlan& pl = g_last_plan;
   out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.main.splits; out8[3] = pl.band_size * pl.cl;

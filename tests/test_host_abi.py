@@ -41,6 +41,43 @@ def test_workspace_sizing_needs_no_gpu():
     assert lib.lr_flatip_workspace_bytes(0, 10, 10) == 0
 
 
+def _plan(Q, N, k):
+    import ctypes
+    out = (ctypes.c_int64 * 16)()
+    assert _C.load().lr_flatip_plan(Q, N, k, out) == 0
+    names = ["cl", "pair", "m_tiles", "n_tiles", "cap", "prefix_tiles", "prefix_splits", "prefix_units", "main_begin",
+             "main_splits", "main_units", "grid", "band", "ws", "rounds", "n_clusters"]
+    return dict(zip(names, list(out)))
+
+
+def test_flatip_plan_invariants():
+    """Host planner (csrc/flatip_topk.cu:make_plan): the two passes partition the corpus tiles, lists are long enough,
+    the grid is whole clusters, and the documented regimes pick the documented variants."""
+    lib = _C.load()
+    for Q, N, k in [(10000, 8_800_000, 100), (10000, 1_100_000, 100), (10000, 8_800_000, 1000), (1, 1_100_000, 100),
+                    (32, 1_100_000, 100), (128, 300, 10), (129, 5000, 2048), (1000, 100_000, 100), (7, 50, 100)]:
+        p = _plan(Q, N, k)
+        assert p["m_tiles"] == -(-Q // 128) and p["n_tiles"] == -(-N // 256)
+        assert p["cap"] >= k + 64 and p["cap"] % 64 == 0
+        assert p["main_begin"] == p["prefix_tiles"] < p["n_tiles"]              # prefix + main cover [0, n_tiles)
+        assert 1 <= p["main_splits"] <= p["n_tiles"] - p["main_begin"]
+        groups = -(-p["m_tiles"] // p["cl"])
+        assert p["main_units"] == groups * p["main_splits"]
+        assert p["prefix_units"] == (groups * p["prefix_splits"] if p["prefix_tiles"] else 0)
+        assert p["grid"] % p["cl"] == 0 and 1 <= p["grid"] <= 148
+        assert p["pair"] in (0, 1) and (not p["pair"] or p["cl"] == 2)
+        assert p["ws"] == lib.lr_flatip_workspace_bytes(Q, N, k) > 0
+    head = _plan(10000, 8_800_000, 100)
+    assert (head["cl"], head["pair"], head["prefix_tiles"], head["cap"]) == (2, 0, 128, 256)   # multicast cluster, 32768-doc prefix
+    big_k = _plan(10000, 8_800_000, 1000)
+    assert (big_k["cl"], big_k["pair"], big_k["cap"]) == (2, 1, 2048) and big_k["prefix_tiles"] == 1000  # pair + 256k-doc prefix
+    online = _plan(32, 1_100_000, 100)
+    assert (online["cl"], online["prefix_tiles"], online["prefix_splits"]) == (1, 148, 148)     # one tile per CTA
+    assert _plan(1, 1_100_000, 100)["prefix_tiles"] == 0                                          # single query: single phase
+    # balanced: the main pass wastes < 3% of its rounds at the headline shape
+    assert head["main_units"] / (head["rounds"] * head["n_clusters"]) > 0.97
+
+
 def test_argument_errors_map_to_value_error():
     lib = _C.load()
     rc = lib.lr_flatip_topk(None, 0, None, 0, 1, 1, 8, None, None, 0, 1, None, None, None, None, 0, None)
