@@ -21,13 +21,56 @@ int topk_merge_strided(const uint64_t* keys, const int32_t* counts, int L, int64
 
 struct PassPlan {
   int tile_begin, tile_end, splits, units, grid, rounds;
+  int sched, band_size, n_bands;  // sched 1: fixed teams per band (band_size groups per full band)
 };
 struct FlatipPlan {
   int cl, pair, m_groups, m_tiles, n_tiles, band_size, n_bands, cap, n_clusters;
   int64_t q_pad;
   PassPlan main, prefix;  // prefix.units == 0 -> single phase
-  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, total_bytes;
+  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, off_teamctr, total_bytes;
 };
+
+// Team schedule of the main pass: bands of g row groups; inside a band the clusters form floor(nc / g) fixed teams, each
+// walking its own splits with one cluster per row group (so a B tile is fetched once per team and the members are kept
+// within a small window by a progress counter).  Picks g and the split count for high cluster utilisation, few corpus
+// passes and an L2-resident A band (<= 40 MB = 20 groups of 2 x 128 rows x 8 KB).
+static bool plan_teams(int m_groups, int nc, int n_tiles_pass, int64_t s_cap, PassPlan& pp) {
+  double best = -1.0;
+  int best_g = 0, best_s = 0;
+  int g_hi = m_groups < 20 ? m_groups : 20, g_lo = m_groups < 4 ? m_groups : 4;
+  const int forced_g = env_int("LR_FLATIP_TEAM_BAND", 0);
+  if (forced_g > 0 && forced_g <= m_groups) g_lo = g_hi = forced_g;
+  for (int g = g_lo; g <= g_hi; ++g) {
+    if (g > nc) break;
+    const int q = m_groups / g, r = m_groups % g;
+    const int n_main = nc / g, n_rem = r ? nc / r : 0;
+    for (int mult = 1; mult <= 64; ++mult) {
+      const int S = n_main * mult;
+      if (S > s_cap || S > n_tiles_pass || S > 96) break;
+      const int64_t time = int64_t(q) * ((S + n_main - 1) / n_main) + (r ? (S + n_rem - 1) / n_rem : 0);
+      const double util = double(m_groups) * S / (double(nc) * double(time));
+      const int passes = q + (r ? 1 : 0);
+      const int64_t tiles_per_split = n_tiles_pass / S;
+      double score = util - 0.012 * passes - (tiles_per_split < 64 ? 0.05 : 0.0) - 0.0002 * S;
+      if (score > best) {
+        best = score;
+        best_g = g;
+        best_s = S;
+      }
+    }
+  }
+  if (best_g == 0) return false;
+  pp.sched = 1;
+  pp.band_size = best_g;
+  pp.n_bands = (m_groups + best_g - 1) / best_g;
+  pp.splits = best_s;
+  pp.units = m_groups * best_s;
+  pp.grid = nc;
+  const int q = m_groups / best_g, r = m_groups % best_g;
+  const int n_main = nc / best_g, n_rem = r ? nc / r : 0;
+  pp.rounds = q * ((best_s + n_main - 1) / n_main) + (r ? (best_s + n_rem - 1) / n_rem : 0);
+  return true;
+}
 
 // corpus splits of one pass: minimise rounds * tiles-per-unit; accept a larger split count only for a >0.5% gain
 static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile_end, int64_t s_cap, int forced) {
@@ -115,6 +158,15 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   if (prefix_tiles > 0)
     pl.prefix = plan_pass(pl.m_groups, geo.n_clusters, 0, prefix_tiles, s_cap, prefix_splits_forced);
   pl.main = plan_pass(pl.m_groups, geo.n_clusters, prefix_tiles, pl.n_tiles, s_cap, env_int("LR_FLATIP_SPLITS", 0));
+  pl.main.band_size = pl.band_size;
+  pl.main.n_bands = pl.n_bands;
+  pl.prefix.band_size = pl.band_size;
+  pl.prefix.n_bands = pl.n_bands;
+  // Large batches: fixed teams (see plan_teams).  LR_FLATIP_SCHED=0 keeps the round-robin schedule.
+  if (env_int("LR_FLATIP_SCHED", 1) != 0 && pl.cl == 2 && pl.m_groups >= 8 && env_int("LR_FLATIP_SPLITS", 0) == 0) {
+    PassPlan tp = pl.main;
+    if (plan_teams(pl.m_groups, geo.n_clusters, pl.n_tiles - prefix_tiles, s_cap, tp)) pl.main = tp;
+  }
 
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   const int main_lists = pl.main.splits + (prefix_tiles > 0 ? 1 : 0);  // + the prefix's merged top-k
@@ -123,7 +175,8 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   pl.off_cand = align(pl.off_counts + size_t(main_lists) * pl.q_pad * 4);
   pl.off_pcounts = align(pl.off_cand + size_t(main_lists) * pl.q_pad * pl.cap * 8);
   pl.off_pcand = align(pl.off_pcounts + size_t(pl.prefix.splits) * pl.q_pad * 4);
-  pl.total_bytes = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.q_pad * pl.cap * 8);
+  pl.off_teamctr = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.q_pad * pl.cap * 8);
+  pl.total_bytes = align(pl.off_teamctr + size_t(pl.main.n_bands) * size_t(pl.main.splits) * 4 + 256);
   return pl;
 }
 
@@ -148,7 +201,10 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
   prm.kblocks = int((d_used + BK - 1) / BK);
   prm.m_tiles = pl.m_tiles; prm.m_groups = pl.m_groups;
   prm.tile_begin = pp.tile_begin; prm.n_tiles = pp.tile_end; prm.splits = pp.splits;
-  prm.band_size = pl.band_size; prm.n_bands = pl.n_bands; prm.units = pp.units;
+  prm.band_size = pp.band_size ? pp.band_size : pl.band_size;  // plan_pass leaves the band layout to the geometry
+  prm.n_bands = pp.band_size ? pp.n_bands : pl.n_bands; prm.units = pp.units;
+  prm.sched = pp.sched;
+  prm.team_window = env_int("LR_FLATIP_TEAM_WINDOW", 1);
   prm.policy_a = l2_policy(env_int("LR_FLATIP_POLICY_A", 0));
   prm.policy_b = l2_policy(env_int("LR_FLATIP_POLICY_B", 0));
   prm.debug_flags = env_int("LR_FLATIP_DEBUG", 0);
@@ -209,14 +265,14 @@ extern "C" int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16) {
   out16[0] = pl.cl; out16[1] = pl.pair; out16[2] = pl.m_tiles; out16[3] = pl.n_tiles; out16[4] = pl.cap;
   out16[5] = pl.prefix.tile_end; out16[6] = pl.prefix.splits; out16[7] = pl.prefix.units;
   out16[8] = pl.main.tile_begin; out16[9] = pl.main.splits; out16[10] = pl.main.units;
-  out16[11] = int64_t(pl.main.grid) * pl.cl; out16[12] = int64_t(pl.band_size) * pl.cl;
+  out16[11] = int64_t(pl.main.grid) * pl.cl; out16[12] = int64_t(pl.main.band_size) * pl.cl;
   out16[13] = int64_t(pl.total_bytes); out16[14] = pl.main.rounds; out16[15] = pl.n_clusters;
   return LR_OK;
 }
 
 extern "C" int lr_flatip_last_plan(int64_t* out8) {
   const FlatipPlan& pl = g_last_plan;
-  out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.main.splits; out8[3] = pl.band_size * pl.cl;
+  out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.main.splits; out8[3] = pl.main.band_size * pl.cl;
   out8[4] = pl.cap; out8[5] = pl.main.grid * pl.cl; out8[6] = pl.main.units; out8[7] = pl.prefix.tile_end;
   return LR_OK;
 }
@@ -275,6 +331,10 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   }
   // ---- phase B / single phase
   fill_params(prm, pl, pl.main, Q, N, d_used);
+  if (pl.main.sched) {
+    prm.team_ctr = reinterpret_cast<uint32_t*>(ws + pl.off_teamctr);
+    LR_CUDA(cudaMemsetAsync(prm.team_ctr, 0, size_t(pl.main.n_bands) * size_t(pl.main.splits) * 4, st));
+  }
   prm.counts = counts;
   prm.cand = cand;
   if ((rc = launch_pass<EPI_TOPK>(pl, pl.main, tmA, tmB, prm, st))) return rc;

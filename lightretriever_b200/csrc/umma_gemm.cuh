@@ -72,6 +72,12 @@ struct GemmParams {
   uint64_t policy_a, policy_b;                     // L2 eviction policy of the A (row) and B (column) tile loads
   int debug_flags;                                 // bit 0: epilogue drops every score (main-loop-only timing)
   int k_rot;                                       // K-block rotation stride per cluster (0 = none), see producer
+  // Team schedule (sched == 1): inside a band the clusters form fixed teams of (groups in the band) clusters; a team
+  // walks its splits together, every member owning one row group, and a progress counter per (band, split) keeps the
+  // members within `team_window` tiles of each other so that a B tile is fetched from HBM once per team.
+  int sched;
+  int team_window;
+  uint32_t* team_ctr;  // [n_bands * splits], zeroed before the launch
   // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
   int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range of [tile_begin, n_tiles)
   int tile_begin;
@@ -104,6 +110,26 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& m_g
   split = rem / mb;
   m_group = b * p.band_size + rem % mb;
 }
+// Visit the units of one cluster: f(m_group, split, team_size, ctr_index).  All three warp roles walk the same sequence.
+template <class F>
+__device__ __forceinline__ void for_each_unit(const GemmParams& p, int cluster_id, int n_clusters, F&& f) {
+  if (p.sched == 0) {  // round robin over (band, split, group in band)
+    for (int u = cluster_id; u < p.units; u += n_clusters) {
+      int m_group, split;
+      decode_unit(p, u, m_group, split);
+      f(m_group, split, 1, 0);
+    }
+  } else {  // fixed teams per band
+    for (int b = 0; b < p.n_bands; ++b) {
+      const int mb = min(p.band_size, p.m_groups - b * p.band_size);
+      const int n_teams = n_clusters / mb;
+      const int team = cluster_id / mb, g = cluster_id - team * mb;
+      if (team >= n_teams) continue;  // this cluster sits the band out
+      for (int split = team; split < p.splits; split += n_teams) f(b * p.band_size + g, split, mb, b * p.splits + split);
+    }
+  }
+}
+
 // columns [c0, c1) covered by a split; tiles start at c0 and step BN
 template <int EPI>
 __device__ __forceinline__ void split_cols(const GemmParams& p, int split, int64_t& c0, int64_t& c1) {
@@ -272,20 +298,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = cluster_id; u < p.units; u += n_clusters) {
-        int m_group, split;
+      for_each_unit(p, cluster_id, n_clusters, [&](int m_group, int split, int team_size, int ctr_index) {
         int64_t c0, c1;
-        decode_unit(p, u, m_group, split);
-        const int m_tile = m_group * CL + cta_rank;  // may be a padding tile (>= m_tiles): TMA zero-fills it
+        int m_tile = m_group * CL + cta_rank;  // may be a padding tile (>= m_tiles): TMA zero-fills it
+        if (p.debug_flags & 4) m_tile = cta_rank;  // traffic experiment: every cluster loads the same A tiles (wrong results)
         split_cols<EPI>(p, split, c0, c1);
         // Clusters that share a B tile (same split) or an A tile (same row group) run in lock step; starting each
         // cluster at a different K block keeps them from requesting the same lines at the same moment (all missing in
         // L2 together) — the first toucher misses, the others hit later.  The sum over K is order-independent.
         const int rot = p.k_rot ? int((unsigned(cluster_id) * unsigned(p.k_rot)) % unsigned(p.kblocks)) : 0;
-        for (int64_t cb = c0; cb < c1; cb += BN) {
+        const bool team_sync = p.sched != 0 && team_size > 1 && cta_rank == 0;
+        uint32_t* ctr = team_sync ? p.team_ctr + ctr_index : nullptr;
+        int ti = 0;
+        for (int64_t cb = c0; cb < c1; cb += BN, ++ti) {
+          if (team_sync && ti >= p.team_window) {
+            // do not run more than team_window tiles ahead of the slowest member of the team
+            const uint32_t need = uint32_t(team_size) * uint32_t(ti - p.team_window + 1);
+            if (ld_acquire_u32(ctr) < need) {
+              const long long t0 = clock64();
+              while (ld_acquire_u32(ctr) < need) {
+                if (clock64() - t0 > LR_MBAR_TIMEOUT_CYCLES) {
+                  printf("lr_b200: team barrier timeout block %d split %d tile %d\n", blockIdx.x, split, ti);
+                  __trap();
+                }
+              }
+            }
+          }
           for (int kbi = 0; kbi < p.kblocks; ++kbi) {
             int kb = kbi + rot;
             if (kb >= p.kblocks) kb -= p.kblocks;
+            const int64_t cbl = (p.debug_flags & 8) ? c0 : cb;  // traffic experiment: B always the unit's first tile
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             if (PAIR) {
@@ -307,15 +349,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
               // my half of the B tile, delivered to both CTAs (same offsets, each CTA's own full barrier)
               tma_load_2d_mc_hint(a_dst + A_BYTES + cta_rank * (B_BYTES / CL), &tmB, kb * BK,
-                                  int(cb) + cta_rank * (BN / CL), full_bar(stage), kMcMask, p.policy_b);
+                                  int(cbl) + cta_rank * (BN / CL), full_bar(stage), kMcMask, p.policy_b);
             }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
+          if (team_sync) red_release_add_u32(ctr, 1u);  // this member has issued tile ti
         }
-      }
+      });
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
@@ -325,10 +368,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = cluster_id; u < p.units; u += n_clusters) {
-        int m_group, split;
+      for_each_unit(p, cluster_id, n_clusters, [&](int m_group, int split, int, int) {
+        (void)m_group;
         int64_t c0, c1;
-        decode_unit(p, u, m_group, split);
         split_cols<EPI>(p, split, c0, c1);
         for (int64_t cb = c0; cb < c1; cb += BN) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -367,7 +409,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             acc_phase ^= 1u;
           }
         }
-      }
+      });
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
@@ -380,10 +422,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t full = 0xFFFFFFFFu;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = cluster_id; u < p.units; u += n_clusters) {
-      int m_group, split;
+    for_each_unit(p, cluster_id, n_clusters, [&](int m_group, int split, int, int) {
       int64_t c0, c1;
-      decode_unit(p, u, m_group, split);
       const int m_tile = m_group * CL + cta_rank;
       split_cols<EPI>(p, split, c0, c1);
       const int64_t row = int64_t(m_tile) * BM + row_in_tile;
@@ -549,7 +589,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.log1p) x = log1pf(x);
         if (row_valid) p.out[seg * p.rows + row] = x;
       }
-    }
+    });
   }
 
   tc_fence_before();

@@ -1,0 +1,77 @@
+"""GPU *library* baseline on the same box and the same data (not the product path): what the headline step costs when
+written with torch.matmul (cuBLAS) + torch.topk over corpus chunks + a concatenated-candidates merge — the
+"recompiled library kernels" the fused tcgen05 kernel has to beat — and the raw cuBLAS GEMM rate on this data under the
+same power cap.  Usage: python tools/gpu_library_baseline.py [--docs N] [--queries Q]"""
+import argparse, json, os, sys, statistics, subprocess, threading
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import lightretriever_b200 as lr
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--docs", type=int, default=8_800_000)
+ap.add_argument("--queries", type=int, default=10_000)
+ap.add_argument("--dim", type=int, default=4096)
+ap.add_argument("--topk", type=int, default=100)
+ap.add_argument("--chunk", type=int, default=131072)
+ap.add_argument("--steps", type=int, default=3)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+N, Q, d, k = a.docs, a.queries, a.dim, a.topk
+corpus = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
+for c0 in range(0, N, 131072):
+    g = torch.Generator(device=dev).manual_seed(1000 + c0 // 131072)
+    n = min(131072, N - c0)
+    corpus[c0:c0 + n] = torch.nn.functional.normalize(torch.randn(131072, d, generator=g, device=dev), dim=-1)[:n].bfloat16()
+q = torch.nn.functional.normalize(torch.randn(Q, d, device=dev), dim=-1).bfloat16()
+
+
+def clocks_run(fn, steps):
+    rows = []
+    p = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits", "-lms", "100"],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    threading.Thread(target=lambda: [rows.append(l) for l in p.stdout], daemon=True).start()
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    p.terminate()
+    mhz = [float(r) for r in rows if r.strip()]
+    return e0.elapsed_time(e1) / steps, (statistics.median(mhz) if mhz else None)
+
+
+def torch_step():
+    best_s = best_i = None
+    for c0 in range(0, N, a.chunk):
+        s = torch.matmul(q, corpus[c0:c0 + a.chunk].T)          # cuBLAS bf16 GEMM, [Q, chunk] bf16
+        ts, ti = torch.topk(s.float(), k, dim=1)
+        ti += c0
+        if best_s is None:
+            best_s, best_i = ts, ti
+        else:
+            cs, ci = torch.cat([best_s, ts], 1), torch.cat([best_i, ti], 1)
+            best_s, mi = torch.topk(cs, k, dim=1)
+            best_i = torch.gather(ci, 1, mi)
+    return best_s, best_i
+
+
+def gemm_only():
+    for c0 in range(0, N, a.chunk):
+        torch.matmul(q, corpus[c0:c0 + a.chunk].T)
+
+
+flops = 2.0 * Q * N * d
+ms, mhz = clocks_run(gemm_only, a.steps)
+print(json.dumps({"what": "cuBLAS bf16 GEMM only (torch.matmul over chunks, scores written to HBM in bf16)", "ms": round(ms, 1),
+                  "tflops": round(flops / ms / 1e9, 1), "sm_mhz": mhz}), flush=True)
+ms, mhz = clocks_run(torch_step, max(1, a.steps - 1))
+print(json.dumps({"what": "torch.matmul + torch.topk per chunk + merge (library baseline of the whole step)", "ms": round(ms, 1),
+                  "qps": round(Q / ms * 1e3, 1), "tflops_equiv": round(flops / ms / 1e9, 1), "sm_mhz": mhz}), flush=True)
+ms, mhz = clocks_run(lambda: lr.flatip_topk(q, corpus, k), a.steps)
+print(json.dumps({"what": "lr_flatip_topk (fused tcgen05 GEMM + top-k, this repo)", "ms": round(ms, 1), "qps": round(Q / ms * 1e3, 1),
+                  "tflops": round(flops / ms / 1e9, 1), "sm_mhz": mhz}), flush=True)
+rs, ri = torch_step()
+s, i = lr.flatip_topk(q, corpus, k)
+print(json.dumps({"ids_identical_to_library_baseline": float((ri == i).float().mean())}), flush=True)
