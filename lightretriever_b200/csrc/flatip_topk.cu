@@ -114,13 +114,17 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   cap = env_int("LR_FLATIP_CAP", cap);
   if (cap < k + 64) cap = k + 64;
   pl.cap = (cap + 63) / 64 * 64;
-  // Kernel variant.  Default: cluster of 2 with multicast B (the most energy-efficient under the power cap).  Long lists
-  // (k > 352: a list no longer fits the 6 KB/warp staging area) run as a cta_group::2 pair with the BIGLIST layout
-  // (4 stages of 32 KB + 22 KB/warp of list staging): there the epilogue, not power, is the limiter — measured at
-  // k=1000, 8.8M docs: 841 ms (multicast) -> 660 ms (pair + BIGLIST + 256k-document prefix).
+  // Kernel variant.  Small batches: cluster of 2 with multicast B.  Long lists (k > 352: a list no longer fits the
+  // 6 KB/warp staging area) run as a cta_group::2 pair with the BIGLIST layout (4 stages of 32 KB + 22 KB/warp of list
+  // staging): there the epilogue is the limiter — measured at k=1000, 8.8M docs: 841 ms (multicast) -> 660 ms (pair +
+  // BIGLIST + 256k-document prefix).  Large batches on the team schedule also run as pairs: once the corpus tiles stay
+  // L2-resident the halved shared-memory traffic of cta_group::2 is what the power cap rewards (same box, 8.8M x 4096,
+  // k=100: 585 ms multicast vs 537 ms pair; profiles/k2_ab_same_box_r1.jsonl).
   int mode = env_int("LR_FLATIP_CLUSTER", 0);
   const bool long_lists = pl.cap > LIST_STAGE_ENTRIES;
-  if (mode == 0 && long_lists && Q > BM) mode = 3;
+  const bool team_sched = env_int("LR_FLATIP_SCHED", 1) != 0 && env_int("LR_FLATIP_SPLITS", 0) == 0 &&
+                          (Q + 2 * BM - 1) / (2 * BM) >= 8;
+  if (mode == 0 && Q > BM && (long_lists || team_sched)) mode = 3;
   const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), mode);
   pl.cl = geo.cl; pl.pair = geo.pair; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
   pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;

@@ -68,7 +68,7 @@ def test_flatip_plan_invariants():
         assert p["pair"] in (0, 1) and (not p["pair"] or p["cl"] == 2)
         assert p["ws"] == lib.lr_flatip_workspace_bytes(Q, N, k) > 0
     head = _plan(10000, 8_800_000, 100)
-    assert (head["cl"], head["pair"], head["prefix_tiles"], head["cap"]) == (2, 0, 128, 256)   # multicast cluster, 32768-doc prefix
+    assert (head["cl"], head["pair"], head["prefix_tiles"], head["cap"]) == (2, 1, 128, 256)   # cta_group::2 pair on the team schedule, 32768-doc prefix
     big_k = _plan(10000, 8_800_000, 1000)
     assert (big_k["cl"], big_k["pair"], big_k["cap"]) == (2, 1, 2048) and big_k["prefix_tiles"] == 1000  # pair + 256k-doc prefix
     online = _plan(32, 1_100_000, 100)
