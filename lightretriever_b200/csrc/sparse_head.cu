@@ -163,7 +163,24 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   int rc;
-  const GemmGeometry geo = plan_geometry(V, env_int("LR_SPARSE_HEAD_BAND", 12), env_int("LR_SPARSE_HEAD_CLUSTER", 0));
+  // a unit covers whole documents and at least ~2 column tiles
+  int sps = int((2 * BN + S - 1) / S);
+  if (sps < 1) sps = 1;
+  sps = env_int("LR_SPARSE_HEAD_DOCS_PER_UNIT", sps);
+  if (sps > B) sps = int(B);
+  const int splits = int((B + sps - 1) / sps);
+  // Vocabulary bands x document splits.  With enough of both, fixed teams of clusters walk the splits of a band in step
+  // (umma_gemm.cuh for_each_unit): a hidden-state tile is fetched from HBM once per team and the band's lm_head rows
+  // stay L2-resident; the team schedule runs as cta_group::2 pairs.  Otherwise round robin over 12-tile bands.
+  int mode = env_int("LR_SPARSE_HEAD_CLUSTER", 0);
+  int team_band = 0;
+  if (env_int("LR_SPARSE_HEAD_SCHED", 1) != 0 && mode != 1 && V > 8 * 2 * BM && splits >= 2) {
+    const int m_groups = int((V + 2 * BM - 1) / (2 * BM));
+    team_band = env_int("LR_SPARSE_HEAD_TEAM_BAND", plan_team_band(m_groups, sm_count() / 2, splits, 0.85));
+    if (team_band > m_groups) team_band = m_groups;
+    if (team_band > 0 && mode == 0) mode = 3;
+  }
+  const GemmGeometry geo = plan_geometry(V, env_int("LR_SPARSE_HEAD_BAND", 12), mode);
   if ((rc = make_tmap(&tmA, W, V, d, d, BM))) return rc;
   if ((rc = make_tmap(&tmB, hidden, B * S, d, d, BN / geo.cl))) return rc;
   GemmParams prm{};
@@ -172,23 +189,38 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   prm.row_pad = int64_t(prm.m_tiles) * BM;
   prm.kblocks = int((d + BK - 1) / BK);
   prm.seg_len = S; prm.n_segs = B;
-  // a unit covers whole documents and at least ~2 column tiles
-  int sps = int((2 * BN + S - 1) / S);
-  if (sps < 1) sps = 1;
-  sps = env_int("LR_SPARSE_HEAD_DOCS_PER_UNIT", sps);
-  if (sps > B) sps = int(B);
   prm.segs_per_split = sps;
-  prm.splits = int((B + sps - 1) / sps);
+  prm.splits = splits;
   prm.band_size = geo.band_size; prm.n_bands = geo.n_bands;
   prm.units = prm.m_groups * prm.splits;
   prm.bias = bias; prm.mask = mask; prm.out = out; prm.relu = relu; prm.log1p = log1p;
   prm.policy_a = l2_policy(env_int("LR_SPARSE_HEAD_POLICY_A", 0));
   prm.policy_b = l2_policy(env_int("LR_SPARSE_HEAD_POLICY_B", 0));
-  const int clusters = prm.units < geo.n_clusters ? prm.units : geo.n_clusters;
+  int clusters = prm.units < geo.n_clusters ? prm.units : geo.n_clusters;
+  uint32_t* team_ctr = nullptr;
+  if (team_band > 0 && geo.cl == 2) {
+    prm.sched = 1;
+    prm.team_window = env_int("LR_SPARSE_HEAD_TEAM_WINDOW", 1);
+    prm.band_size = team_band;
+    prm.n_bands = (prm.m_groups + team_band - 1) / team_band;
+    clusters = geo.n_clusters;
+    // progress counters of the teams, one per (band, split): stream-ordered scratch, released after the launch
+    const size_t ctr_bytes = size_t(prm.n_bands) * size_t(prm.splits) * 4;
+    LR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&team_ctr), ctr_bytes, st));
+    cudaError_t e = cudaMemsetAsync(team_ctr, 0, ctr_bytes, st);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(team_ctr, st);
+      set_error("sparse_head: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+      return LR_ECUDA;
+    }
+    prm.team_ctr = team_ctr;
+  }
   const int grid = clusters * geo.cl;
-  if (geo.pair) return launch_umma_gemm<EPI_MAXTOK, 2, true>(tmA, tmB, prm, grid, st);
-  return geo.cl == 2 ? launch_umma_gemm<EPI_MAXTOK, 2>(tmA, tmB, prm, grid, st)
-                     : launch_umma_gemm<EPI_MAXTOK, 1>(tmA, tmB, prm, grid, st);
+  if (geo.pair) rc = launch_umma_gemm<EPI_MAXTOK, 2, true>(tmA, tmB, prm, grid, st);
+  else rc = geo.cl == 2 ? launch_umma_gemm<EPI_MAXTOK, 2>(tmA, tmB, prm, grid, st)
+                        : launch_umma_gemm<EPI_MAXTOK, 1>(tmA, tmB, prm, grid, st);
+  if (team_ctr) cudaFreeAsync(team_ctr, st);
+  return rc;
 }
 
 extern "C" size_t lr_sparsify_scratch_bytes(int64_t B, int64_t V) {

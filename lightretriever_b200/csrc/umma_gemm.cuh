@@ -716,4 +716,24 @@ inline GemmGeometry plan_geometry(int64_t rows, int band_max_tiles, int mode) {
   return g;
 }
 
+// Team schedule for a fixed number of splits: the band width g (row groups per band) that keeps the most clusters busy
+// when each band's floor(nc / g) teams share `splits` splits.  Returns 0 when no width reaches `min_util`.
+inline int plan_team_band(int m_groups, int nc, int splits, double min_util, int g_max = 20) {
+  double best = min_util;
+  int best_g = 0;
+  const int g_hi = m_groups < g_max ? m_groups : g_max;
+  for (int g = (m_groups < 4 ? m_groups : 4); g <= g_hi && g <= nc; ++g) {
+    const int q = m_groups / g, r = m_groups % g;
+    const int n_main = nc / g, n_rem = r ? nc / r : 0;
+    const int64_t time = int64_t(q) * ((splits + n_main - 1) / n_main) + (r ? (splits + n_rem - 1) / n_rem : 0);
+    const double util = double(m_groups) * splits / (double(nc) * double(time));
+    const double score = util - 0.0005 * (q + (r ? 1 : 0));  // ties: fewer passes over the column operand
+    if (score > best) {
+      best = score;
+      best_g = g;
+    }
+  }
+  return best_g;
+}
+
 }  // namespace lr

@@ -292,6 +292,30 @@ def test_sparse_head_vs_oracle(B, S, d, V):
             assert abs(gj[t] - ej[t]) <= max(1, 0.01 * ej[t])
 
 
+@pytest.mark.parametrize("window", [1, 3])
+def test_sparse_head_team_schedule_matches_round_robin(monkeypatch, window):
+    """The team schedule (fixed cluster teams per vocabulary band + progress window) only reorders units: results are
+    bit-identical to the round-robin schedule and match the oracle."""
+    B, S, d, V = 6, 128, 256, 9000
+    gen = torch.Generator().manual_seed(window)
+    h = torch.randn(B, S, d, generator=gen).bfloat16()
+    W = (torch.randn(V, d, generator=gen) * 0.05).bfloat16()
+    lens = torch.randint(3, S + 1, (B,), generator=gen)
+    mask = (torch.arange(S)[None] < lens[:, None])
+    monkeypatch.setenv("LR_SPARSE_HEAD_DOCS_PER_UNIT", "1")
+    monkeypatch.setenv("LR_SPARSE_HEAD_SCHED", "0")
+    rr = lr.max_linear_mapping(h.cuda(), W.cuda(), None, mask.cuda(), relu=True, log1p=True, weight_is_vd=True)
+    monkeypatch.setenv("LR_SPARSE_HEAD_SCHED", "1")
+    monkeypatch.setenv("LR_SPARSE_HEAD_TEAM_BAND", "8")   # 36 row groups -> 4 full bands of 9 teams + a 4-group band
+    monkeypatch.setenv("LR_SPARSE_HEAD_TEAM_WINDOW", str(window))
+    for mode in ("2", "3"):                                  # multicast cluster, cta_group::2 pair
+        monkeypatch.setenv("LR_SPARSE_HEAD_CLUSTER", mode)
+        got = lr.max_linear_mapping(h.cuda(), W.cuda(), None, mask.cuda(), relu=True, log1p=True, weight_is_vd=True)
+        assert torch.equal(got, rr)
+    ref = torch.log1p(torch.relu(oracle.max_linear_map(h.float(), W.float().T, None, mask)))
+    torch.testing.assert_close(rr.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
 def test_quantiser_golden_bit_exact(golden_dir):
     g = np.load(os.path.join(golden_dir, "quantize.npz"))
     got = lr.convert_sparse_reps_to_json(torch.from_numpy(g["reps"]).cuda(), quantization_factor=100)
