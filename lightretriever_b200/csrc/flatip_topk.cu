@@ -180,7 +180,7 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   pl.off_pcounts = align(pl.off_cand + size_t(main_lists) * pl.q_pad * pl.cap * 8);
   pl.off_pcand = align(pl.off_pcounts + size_t(pl.prefix.splits) * pl.q_pad * 4);
   pl.off_teamctr = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.q_pad * pl.cap * 8);
-  pl.total_bytes = align(pl.off_teamctr + size_t(pl.main.n_bands) * size_t(pl.main.splits) * 4 + 256);
+  pl.total_bytes = align(pl.off_teamctr + size_t(pl.main.n_bands) * size_t(pl.n_clusters) * 4 + 256);
   return pl;
 }
 
@@ -337,7 +337,7 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   fill_params(prm, pl, pl.main, Q, N, d_used);
   if (pl.main.sched) {
     prm.team_ctr = reinterpret_cast<uint32_t*>(ws + pl.off_teamctr);
-    LR_CUDA(cudaMemsetAsync(prm.team_ctr, 0, size_t(pl.main.n_bands) * size_t(pl.main.splits) * 4, st));
+    LR_CUDA(cudaMemsetAsync(prm.team_ctr, 0, size_t(pl.main.n_bands) * size_t(pl.n_clusters) * 4, st));
   }
   prm.counts = counts;
   prm.cand = cand;

@@ -204,8 +204,8 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
     prm.band_size = team_band;
     prm.n_bands = (prm.m_groups + team_band - 1) / team_band;
     clusters = geo.n_clusters;
-    // progress counters of the teams, one per (band, split): stream-ordered scratch, released after the launch
-    const size_t ctr_bytes = size_t(prm.n_bands) * size_t(prm.splits) * 4;
+    // progress counters of the teams, one per (band, team): stream-ordered scratch, released after the launch
+    const size_t ctr_bytes = size_t(prm.n_bands) * size_t(geo.n_clusters) * 4;
     LR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&team_ctr), ctr_bytes, st));
     cudaError_t e = cudaMemsetAsync(team_ctr, 0, ctr_bytes, st);
     if (e != cudaSuccess) {

@@ -77,7 +77,7 @@ struct GemmParams {
   // members within `team_window` tiles of each other so that a B tile is fetched from HBM once per team.
   int sched;
   int team_window;
-  uint32_t* team_ctr;  // [n_bands * splits], zeroed before the launch
+  uint32_t* team_ctr;  // [n_bands * n_clusters] tiles issued per (band, team), zeroed before the launch
   // column split geometry: split s covers columns [s*cols_per_split_num/den ...) — see split_cols()
   int n_tiles;          // EPI_STORE / EPI_TOPK: 256-column tiles, split = balanced tile range of [tile_begin, n_tiles)
   int tile_begin;
@@ -125,7 +125,7 @@ __device__ __forceinline__ void for_each_unit(const GemmParams& p, int cluster_i
       const int n_teams = n_clusters / mb;
       const int team = cluster_id / mb, g = cluster_id - team * mb;
       if (team >= n_teams) continue;  // this cluster sits the band out
-      for (int split = team; split < p.splits; split += n_teams) f(b * p.band_size + g, split, mb, b * p.splits + split);
+      for (int split = team; split < p.splits; split += n_teams) f(b * p.band_size + g, split, mb, b * n_clusters + team);
     }
   }
 }
@@ -298,6 +298,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int team_slot = -1, ti = 0;  // progress counter in use and tiles issued against it (cumulative over the units)
       for_each_unit(p, cluster_id, n_clusters, [&](int m_group, int split, int team_size, int ctr_index) {
         int64_t c0, c1;
         int m_tile = m_group * CL + cta_rank;  // may be a padding tile (>= m_tiles): TMA zero-fills it
@@ -309,7 +310,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int rot = p.k_rot ? int((unsigned(cluster_id) * unsigned(p.k_rot)) % unsigned(p.kblocks)) : 0;
         const bool team_sync = p.sched != 0 && team_size > 1 && cta_rank == 0;
         uint32_t* ctr = team_sync ? p.team_ctr + ctr_index : nullptr;
-        int ti = 0;
+        if (ctr_index != team_slot) {
+          team_slot = ctr_index;
+          ti = 0;
+        }
         for (int64_t cb = c0; cb < c1; cb += BN, ++ti) {
           if (team_sync && ti >= p.team_window) {
             // do not run more than team_window tiles ahead of the slowest member of the team
