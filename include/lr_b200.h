@@ -180,9 +180,10 @@ int lr_sparsify_quantize(const float* reps, int64_t B, int64_t V, int top_k, int
  *   Only documents with score > 0 are returned (Lucene returns matching docs only);
  *   missing tail = (-inf, -1). Scores are exact integers (returned as f32; exact < 2^24).
  * ------------------------------------------------------------------------- */
-/* Documents are scored in blocks of lr_sparse_block_docs() (16384) consecutive ids whose int32 accumulators
- * live in shared memory.  blockptr[t*(nblk+1) + b] = number of postings of token t with doc < b*block_docs
- * (nblk = ceil(N / block_docs)); built once per index (index time, not on the query path). */
+/* Documents are scored in blocks of lr_sparse_block_docs() (4096) consecutive ids whose int32 accumulators
+ * live in shared memory, one block per warp.  blockptr[t*(nblk+1) + b] = number of postings of token t with
+ * doc < b*block_docs (nblk = ceil(N / block_docs)); built once per index (index time, not on the query path).
+ * Query terms with a count <= 0 contribute nothing. */
 int    lr_sparse_block_docs(void);
 int    lr_sparse_build_blockptr(const int64_t* post_indptr, const int32_t* post_doc, int64_t V, int64_t N,
                                 uint32_t* blockptr /* [V*(nblk+1)] */, void* stream);

@@ -5,25 +5,29 @@
 // -pretokenized).  Score definition: scripts/asymmetric_sparse_infer.ipynb:207-228
 //     score(q, d) = sum_{t in q ∩ d} count_q(t) * impact_d(t)        (integer arithmetic)
 //
-// HBM-bound gather-accumulate.  Documents are processed in blocks of 16384 consecutive ids whose int32
-// accumulators live in shared memory (never in HBM).  A unit = (query, range of document blocks).  Per block:
-//   1. every query term looks up its posting sub-range [blockptr[t][b], blockptr[t][b+1]) (no search);
-//   2. the sub-ranges are flattened and all 256 threads stream (doc, impact) pairs with independent,
-//      coalesced loads and atomicAdd count*impact into shared memory;
-//   3. only the accumulators touched in this block are visited (the first atomicAdd that finds 0 records the
-//      slot in a shared-memory list; > 4096 touches fall back to a full scan); entries beating the unit's running
-//      threshold (a full 64-bit (score, ~id) key) are appended to a shared-memory candidate list; when the list
-//      would overflow, a block-wide 64-bit radix select cuts list ∪ block back to the exact top-k and raises the
-//      threshold.
-// The unit's list goes to the workspace and lr_topk_merge produces the sorted result.
+// Gather-accumulate with warp-granular workers.  Documents are processed in blocks of SS_BLOCK_DOCS consecutive ids;
+// every WARP is an independent worker with its own int32 accumulator block, candidate list, histogram and touched
+// list in shared memory, so the kernel has no block-wide barrier at all and the dependent chain of one step
+// (block pointers -> postings -> shared-memory atomics -> visit) is hidden by the other resident warps.
+// A unit = (query, range of document blocks), handed out dynamically (one global atomic per unit).  Per step:
+//   1. lane t owns query term t and walks its row of blockptr with a two-block-ahead prefetch: the posting
+//      sub-range [blockptr[t][b], blockptr[t][b+1]) costs no search and no exposed latency;
+//   2. the sub-ranges are flattened (warp scan + shuffle binary search) and streamed in batches of
+//      SS_BATCH x 32 postings: all loads of a batch are issued before its shared-memory atomicAdds;
+//   3. the first add that finds 0 records the slot, so only touched accumulators are visited (a step touching more
+//      than SS_TOUCH_CAP slots scans the block); entries beating the unit's running 64-bit threshold key — and the
+//      query's global score floor, raised with atomicMax by every unit of that query — are appended to the warp's
+//      candidate list; a full list is cut to its exact top-k by a warp-level 64-bit radix select.
+// The unit's list goes to the workspace and lr_topk_merge produces the sorted result.  Integer-exact.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lr {
 
-constexpr int SS_THREADS = 256;
-constexpr int SS_BLOCK_DOCS = 16384;
-constexpr int SS_TERM_CHUNK = 256;
-constexpr int SS_TOUCH_CAP = 4096;  // touched-accumulator list; a block that touches more falls back to a full scan
+constexpr int SS_TOUCH_CAP = 512;  // touched-accumulator list per warp; a step that touches more scans the block
+constexpr int SS_BATCH = 4;        // postings per lane whose loads are in flight together
+constexpr int SS_MAX_WARPS = 20;
 
 struct SSParams {
   const int32_t* q_indptr;
@@ -35,253 +39,299 @@ struct SSParams {
   const uint16_t* post_imp;
   const uint32_t* blockptr;
   int64_t V, N;
-  int nblk, S, k, cap;
-  uint64_t* cand;   // [S][Q][cap]
-  int32_t* counts;  // [S][Q]
+  int nblk, S, k, cap, warp_bytes;
+  uint64_t* cand;     // [S][Q][cap]
+  int32_t* counts;    // [S][Q]
+  uint32_t* floor_q;  // [Q] score floor of each query (k-th best score some unit has proven), zeroed per launch
+  uint32_t* next_unit;  // dynamic unit counter, zeroed per launch
+  uint32_t* overflow;   // set by the 16-bit pass when an accumulator would exceed 65535; the 32-bit pass runs only then
 };
 
-__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int incl = v;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-    if (lane >= off) incl += t;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  int before = 0, tot = 0;
-#pragma unroll
-  for (int w = 0; w < SS_THREADS / 32; ++w) {
-    const int t = warp_sums[w];
-    if (w < warp) before += t;
-    tot += t;
-  }
-  total = tot;
-  __syncthreads();
-  return before + incl - v;
+// Accumulator access.  AccT = uint16_t packs two documents per shared-memory word (twice the resident warps for the same
+// block size); a sum that would not fit raises `ovf` and the launch is repeated with int32 accumulators.
+template <typename AccT>
+__device__ __forceinline__ bool acc_add_first(AccT* acc, int slot, int add, bool& ovf);
+template <>
+__device__ __forceinline__ bool acc_add_first<int32_t>(int32_t* acc, int slot, int add, bool&) {
+  return atomicAdd(&acc[slot], add) == 0;
+}
+template <>
+__device__ __forceinline__ bool acc_add_first<uint16_t>(uint16_t* acc, int slot, int add, bool& ovf) {
+  const int sh = (slot & 1) * 16;
+  const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(acc) + (slot >> 1), uint32_t(add) << sh);
+  const uint32_t old16 = (old >> sh) & 0xFFFFu;
+  ovf |= old16 + uint32_t(add) > 0xFFFFu;
+  return old16 == 0;
 }
 
-__global__ void __launch_bounds__(SS_THREADS)
+// Exact cut of list[0..n) (n > k) to its k largest keys, in place; returns the new threshold key (every kept key is
+// >= it, every dropped key < it).  One warp; hist = 256 words of this warp's shared memory.  Out of line: it runs a few
+// times per unit and must not bloat the step loop's instruction footprint.
+__device__ __noinline__ uint64_t warp_cut_topk(uint64_t* list, uint32_t* n_io, int k, uint32_t* hist) {
+  const uint32_t full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = *n_io;
+  uint64_t prefix = 0, kstar = 0;
+  uint32_t remaining = uint32_t(k);
+  for (int pass = 7; pass >= 0; --pass) {
+    const int shift = pass * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint64_t key = list[i];
+      if (pass == 7 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+    }
+    __syncwarp();
+    uint32_t bin, rem2;
+    bool take_all;
+    warp_find_bin_desc(hist, remaining, bin, rem2, take_all);
+    __syncwarp();
+    prefix = (prefix << 8) | uint64_t(bin);
+    remaining = rem2;
+    if (take_all || pass == 0) {
+      kstar = prefix << shift;
+      break;
+    }
+  }
+  uint32_t m = 0;
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const uint64_t key = i < n ? list[i] : 0ull;
+    const bool keep = i < n && key >= kstar;
+    const uint32_t km = __ballot_sync(full, keep);
+    __syncwarp();
+    if (keep) list[m + __popc(km & lanemask_lt())] = key;
+    m += __popc(km);
+    __syncwarp();
+  }
+  *n_io = m;
+  return kstar;
+}
+
+template <int BD, int NB, typename AccT>
+__global__ void __launch_bounds__(SS_MAX_WARPS * 32, 1)
 sparse_score_kernel(const SSParams p) {
+  if (sizeof(AccT) == 4 && p.overflow && ld_relaxed_u32(p.overflow) == 0) return;  // the 16-bit pass was exact
   extern __shared__ __align__(16) uint8_t ss_smem[];
-  int32_t* acc = reinterpret_cast<int32_t*>(ss_smem);
-  uint64_t* list = reinterpret_cast<uint64_t*>(ss_smem + size_t(SS_BLOCK_DOCS) * 4);
-  uint64_t* other = list + p.cap;
-  int64_t* t_start = reinterpret_cast<int64_t*>(other + p.cap);
-  int32_t* t_pre = reinterpret_cast<int32_t*>(t_start + SS_TERM_CHUNK);
-  int32_t* t_w = t_pre + SS_TERM_CHUNK;
-  uint16_t* touched = reinterpret_cast<uint16_t*>(t_w + SS_TERM_CHUNK);  // [SS_TOUCH_CAP] accumulators written this block
-  __shared__ uint32_t hist[256];
-  __shared__ int warp_sums[SS_THREADS / 32];
-  __shared__ uint32_t s_n, s_nt, s_bin, s_rem, s_take;
-  const int tid = threadIdx.x;
+  const uint32_t full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  uint8_t* wbase = ss_smem + size_t(warp) * p.warp_bytes;
+  AccT* acc = reinterpret_cast<AccT*>(wbase);
+  uint64_t* list = reinterpret_cast<uint64_t*>(wbase + size_t(BD) * sizeof(AccT));
+  uint32_t* hist = reinterpret_cast<uint32_t*>(list + p.cap);
+  uint16_t* touched = reinterpret_cast<uint16_t*>(hist + 256);
 
-  for (int i = tid; i < SS_BLOCK_DOCS; i += SS_THREADS) acc[i] = 0;
-  if (tid == 0) s_nt = 0;
-  __syncthreads();
+  for (int i = lane; i < BD; i += 32) acc[i] = 0;
+  __syncwarp();
 
-  const int64_t n_units = p.Q * p.S;
-  for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-    const int64_t q = u / p.S;
-    const int s = int(u % p.S);
+  const uint32_t n_units = uint32_t(p.Q * p.S);
+  for (;;) {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(p.next_unit, 1u);
+    u = __shfl_sync(full, u, 0);
+    if (u >= n_units) break;
+    const int64_t q = u / uint32_t(p.S);
+    const int s = int(u % uint32_t(p.S));
     const int b0 = int((int64_t(s) * p.nblk) / p.S);
     const int b1 = int((int64_t(s + 1) * p.nblk) / p.S);
     const int qt0 = p.q_indptr[q];
     const int nterms = p.q_indptr[q + 1] - qt0;
-    uint32_t n = 0;                    // entries in `list` (uniform copy of s_n between blocks)
-    uint64_t thr = 0xFFFFFFFFull;      // candidates need key > thr; every score-0 key is <= this
-    if (tid == 0) s_n = 0;
-    // fast path (<= 256 query terms, the normal case): every thread owns one term and walks its block pointers with a
-    // one-block-ahead prefetch, so the term set-up of a block costs no exposed global latency
-    const bool one_chunk = nterms <= SS_TERM_CHUNK;
+    // a step = (document block, chunk of 32 query terms); lane t owns term t of the chunk.  Queries of <= 32 terms (the
+    // normal case) walk their blockptr rows with a two-block-ahead prefetch; longer ones fetch the pointers per step.
+    const int nchunks = nterms > 32 ? (nterms + 31) >> 5 : 1;
+    const bool one_chunk = nchunks == 1;
+    const int nsteps = (b1 - b0) * nchunks;
+    uint32_t n = 0;                // entries in `list` (warp-uniform)
+    uint64_t thr = 0xFFFFFFFFull;  // candidates need key > thr; every score-0 key is <= this
+    uint32_t ntouch = 0;           // accumulators touched in the current block (warp-uniform)
+    bool ovf = false;
+
     const uint32_t* bp_row = nullptr;
     int64_t post_base = 0;
-    int my_w = 0;
     uint32_t lo = 0, hi = 0, nxt = 0;
-    if (one_chunk && tid < nterms) {
-      const int t = p.q_tok[qt0 + tid];
-      if (t >= 0 && t < p.V) {
+    int w_cur = 0;  // this lane's term weight for the batch waiting in registers
+    if (one_chunk && lane < nterms) {
+      const int t = p.q_tok[qt0 + lane];
+      const int w = p.q_cnt[qt0 + lane];
+      if (t >= 0 && t < p.V && w > 0) {  // terms with a count <= 0 contribute nothing
         bp_row = p.blockptr + int64_t(t) * (p.nblk + 1);
         post_base = p.post_indptr[t];
-        my_w = p.q_cnt[qt0 + tid];
+        w_cur = w;
         lo = bp_row[b0];
         hi = bp_row[b0 + 1];
         nxt = (b0 + 2 <= p.nblk) ? bp_row[b0 + 2] : hi;
       }
     }
-    __syncthreads();
+    // flatten state of the batch waiting in registers, and the batch itself (NB postings per lane)
+    int total = 0, pre = 0;
+    int64_t rel = 0;  // posting index of flattened position j inside this lane's term = rel + j
+    int doc[NB], imp[NB], tl[NB];
+    int pb = b0, pc = 0;  // step the next load phase fetches
+    int ab = b0, ac = 0;  // step of the waiting batch
+    uint32_t floor_s = 0;
 
-    for (int b = b0; b < b1; ++b) {
-      const int64_t d0 = int64_t(b) * SS_BLOCK_DOCS;
-      // ---- 1+2: accumulate the block's postings
-      for (int tc = 0; tc < nterms; tc += SS_TERM_CHUNK) {
+    // largest l in [0, 32) with pre[l] <= j (lanes past the last term hold pre == total > j)
+    auto find_term = [&](int j) {
+      int l = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int pv = __shfl_sync(full, pre, l + step);
+        if (pv <= j) l += step;
+      }
+      return l;
+    };
+    // the first add that finds 0 records the slot
+    auto note_first = [&](bool first, int slot) {
+      const uint32_t fm = __ballot_sync(full, first);
+      const uint32_t tpos = ntouch + __popc(fm & lt);
+      if (first && tpos < SS_TOUCH_CAP) touched[tpos] = uint16_t(slot);
+      ntouch += __popc(fm);
+    };
+
+    for (int e = -1; e < nsteps; ++e) {
+      if (e >= 0) {
+        // ---- accumulate the waiting batch: all atomics first, then the first-touch bookkeeping
+        const int d0 = ab * BD;
+        if (ac == 0 && p.S > 1) floor_s = ld_relaxed_u32(p.floor_q + q);  // consumed by the visit
+        bool fst[NB];
+        int slot[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          fst[i] = false;
+          slot[i] = doc[i] - d0;
+          if (i * 32 < total) {  // warp-uniform
+            const int add = __shfl_sync(full, w_cur, tl[i]) * imp[i];
+            if (add != 0) fst[i] = acc_add_first<AccT>(acc, slot[i], add, ovf);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+          if (i * 32 < total) note_first(fst[i], slot[i]);
+        // postings beyond the register batch (long posting runs): direct
+        for (int j0 = 32 * NB; j0 < total; j0 += 32) {
+          const int j = min(j0 + lane, total - 1);
+          const int l = find_term(j);
+          const int64_t idx = __shfl_sync(full, rel, l) + j;
+          const int wl = __shfl_sync(full, w_cur, l);
+          const int sl = __ldg(p.post_doc + idx) - d0;
+          const int add = j0 + lane < total ? wl * int(__ldg(p.post_imp + idx)) : 0;
+          bool first = false;
+          if (add != 0) first = acc_add_first<AccT>(acc, sl, add, ovf);
+          note_first(first, sl);
+        }
+      }
+      if (e + 1 < nsteps) {
+        // ---- load phase of the next step: its postings are in flight while the current block is visited
         int cnt = 0;
+        int64_t start = 0;
         if (one_chunk) {
           if (bp_row) {
-            t_start[tid] = post_base + lo;
+            start = post_base + lo;
             cnt = int(hi - lo);
-            t_w[tid] = my_w;
             lo = hi;
             hi = nxt;
-            if (b + 3 <= p.nblk && b + 1 < b1) nxt = bp_row[b + 3];  // consumed two blocks from now
+            if (pb + 3 <= p.nblk && pb + 2 < b1) nxt = bp_row[pb + 3];  // consumed two blocks from now
           }
         } else {
-          const int i = tc + tid;
+          const int i = pc * 32 + lane;
+          w_cur = 0;
           if (i < nterms) {
             const int t = p.q_tok[qt0 + i];
-            if (t >= 0 && t < p.V) {
-              const uint32_t* bp = p.blockptr + int64_t(t) * (p.nblk + 1) + b;
+            const int wi = p.q_cnt[qt0 + i];
+            if (t >= 0 && t < p.V && wi > 0) {
+              const uint32_t* bp = p.blockptr + int64_t(t) * (p.nblk + 1) + pb;
               const uint32_t l2 = bp[0], h2 = bp[1];
-              t_start[tid] = p.post_indptr[t] + l2;
+              start = p.post_indptr[t] + l2;
               cnt = int(h2 - l2);
-              t_w[tid] = p.q_cnt[qt0 + i];
+              w_cur = wi;
             }
           }
         }
-        int total;
-        const int pre = block_exclusive_scan(cnt, warp_sums, total);
-        t_pre[tid] = pre;
-        __syncthreads();
-        const int nt = min(SS_TERM_CHUNK, nterms - tc);
-        for (int j = tid; j < total; j += SS_THREADS) {
-          // largest i in [0, nt) with t_pre[i] <= j
-          int l = 0, h = nt - 1;
-          while (l < h) {
-            const int mid = (l + h + 1) >> 1;
-            if (t_pre[mid] <= j) l = mid; else h = mid - 1;
-          }
-          const int64_t idx = t_start[l] + (j - t_pre[l]);
-          const int doc = __ldg(p.post_doc + idx);
-          const int add = t_w[l] * int(__ldg(p.post_imp + idx));
-          const int slot = doc - int(d0);
-          // first touch of this accumulator in this block -> remember the slot (one shared-counter atomic per warp)
-          const bool first = add != 0 && atomicAdd(&acc[slot], add) == 0;
-          const unsigned am = __activemask();
-          const unsigned fm = __ballot_sync(am, first);
-          if (fm) {
-            const int leader = __ffs(fm) - 1;
-            uint32_t tbase = 0;
-            if ((tid & 31) == leader) tbase = atomicAdd(&s_nt, uint32_t(__popc(fm)));
-            tbase = __shfl_sync(am, tbase, leader);
-            if (first) {
-              const uint32_t tpos = tbase + __popc(fm & ((1u << (tid & 31)) - 1u));
-              if (tpos < SS_TOUCH_CAP) touched[tpos] = uint16_t(slot);
-            }
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(full, incl, off);
+          if (lane >= off) incl += t;
+        }
+        total = __shfl_sync(full, incl, 31);
+        pre = incl - cnt;
+        rel = start - pre;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          if (i * 32 < total) {  // warp-uniform
+            const int j = min(i * 32 + lane, total - 1);  // lanes past the end repeat the last posting's address
+            const int l = find_term(j);
+            const int64_t idx = __shfl_sync(full, rel, l) + j;
+            tl[i] = l;
+            doc[i] = __ldg(p.post_doc + idx);
+            imp[i] = i * 32 + lane < total ? int(__ldg(p.post_imp + idx)) : 0;
           }
         }
-        __syncthreads();
+        if (++pc == nchunks) {
+          pc = 0;
+          ++pb;
+        }
       }
-      // ---- 3: visit the touched accumulators (or all of them when the touched list overflowed)
-      const uint32_t nt_all = s_nt;
-      const bool dense = nt_all > SS_TOUCH_CAP;
-      const int n_visit = dense ? SS_BLOCK_DOCS : int(nt_all);
-      auto slot_of = [&](int i) -> int { return dense ? i : int(touched[i]); };
-      int c = 0;
-      for (int i = tid; i < n_visit; i += SS_THREADS) {
-        const int sl = slot_of(i);
-        const int sc = acc[sl];
-        if (sc > 0 && make_key(uint32_t(sc), uint32_t(d0 + sl)) > thr) ++c;
-      }
-      uint32_t base = c ? atomicAdd(&s_n, uint32_t(c)) : 0u;
-      __syncthreads();
-      const uint32_t total_n = s_n;
-      if (total_n <= uint32_t(p.cap)) {
-        for (int i = tid; i < n_visit; i += SS_THREADS) {
-          const int sl = slot_of(i);
-          const int sc = acc[sl];
-          if (sc != 0) {
-            acc[sl] = 0;
+      if (e >= 0) {
+        if (ac == nchunks - 1) {
+          // ---- visit the touched accumulators of block ab (or all of them when the touched list overflowed)
+          __syncwarp();
+          const int d0 = ab * BD;
+          const bool dense = ntouch > SS_TOUCH_CAP;
+          const uint32_t n_visit = dense ? uint32_t(BD) : ntouch;
+          for (uint32_t i0 = 0; i0 < n_visit; i0 += 32) {
+            const uint32_t i = min(i0 + lane, n_visit - 1);
+            const int sl = dense ? int(i) : int(touched[i]);
+            const int sc = i0 + lane < n_visit ? int(acc[sl]) : 0;
+            if (sc != 0) acc[sl] = 0;
             const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + sl));
-            if (sc > 0 && key > thr) list[base++] = key;
-          }
-        }
-        n = total_n;
-      } else {
-        // ---- overflow: exact k-th largest key of list[0..n) ∪ {block candidates}, then rebuild
-        uint64_t prefix = 0;
-        uint32_t remaining = uint32_t(p.k);
-        uint64_t kstar = 0;
-        for (int pass = 7; pass >= 0; --pass) {
-          const int shift = pass * 8;
-          hist[tid] = 0;
-          __syncthreads();
-          for (uint32_t i = tid; i < n; i += SS_THREADS) {
-            const uint64_t key = list[i];
-            if (pass == 7 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
-          }
-          for (int i = tid; i < n_visit; i += SS_THREADS) {
-            const int sl = slot_of(i);
-            const int sc = acc[sl];
-            if (sc > 0) {
-              const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + sl));
-              if (key > thr && (pass == 7 || (key >> (shift + 8)) == prefix))
-                atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+            bool pass = uint32_t(sc) >= floor_s && key > thr;  // key > thr implies sc > 0
+            uint32_t pm = __ballot_sync(full, pass);
+            while (pm) {
+              const uint32_t room = uint32_t(p.cap) - n;
+              const uint32_t rank = __popc(pm & lt);
+              if (pass && rank < room) {
+                list[n + rank] = key;
+                pass = false;
+              }
+              n += min(uint32_t(__popc(pm)), room);
+              __syncwarp();
+              if (n == uint32_t(p.cap)) {
+                thr = warp_cut_topk(list, &n, p.k, hist);
+                if (p.S > 1 && lane == 0) atomicMax(p.floor_q + q, key_hi(thr));
+                pass = pass && key > thr;
+              }
+              pm = __ballot_sync(full, pass);
             }
           }
-          __syncthreads();
-          if (tid < 32) {
-            uint32_t bin, rem2;
-            bool take_all;
-            warp_find_bin_desc(hist, remaining, bin, rem2, take_all);
-            if (tid == 0) {
-              s_bin = bin;
-              s_rem = rem2;
-              s_take = take_all ? 1u : 0u;
-            }
-          }
-          __syncthreads();
-          prefix = (prefix << 8) | uint64_t(s_bin);
-          remaining = s_rem;
-          const bool take_all = s_take != 0;
-          __syncthreads();
-          if (take_all || pass == 0) {
-            kstar = prefix << shift;
-            break;
-          }
+          ntouch = 0;
+          __syncwarp();
+          ac = 0;
+          ++ab;
+        } else {
+          ++ac;
         }
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += SS_THREADS) {
-          const uint64_t key = list[i];
-          if (key >= kstar) other[atomicAdd(&s_n, 1u)] = key;
-        }
-        for (int i = tid; i < n_visit; i += SS_THREADS) {
-          const int sl = slot_of(i);
-          const int sc = acc[sl];
-          if (sc != 0) {
-            acc[sl] = 0;
-            const uint64_t key = make_key(uint32_t(sc), uint32_t(d0 + sl));
-            if (sc > 0 && key > thr && key >= kstar) other[atomicAdd(&s_n, 1u)] = key;
-          }
-        }
-        __syncthreads();
-        uint64_t* tmp = list;
-        list = other;
-        other = tmp;
-        n = s_n;  // == k
-        thr = kstar;
       }
-      __syncthreads();
-      if (tid == 0) s_nt = 0;
-      // (the next block's first __syncthreads orders this reset before any new touch)
     }
+    if (sizeof(AccT) == 2 && __any_sync(full, ovf) && lane == 0) atomicOr(p.overflow, 1u);
     // ---- unit result
     uint64_t* dst = p.cand + (int64_t(s) * p.Q + q) * p.cap;
-    for (uint32_t i = tid; i < n; i += SS_THREADS) dst[i] = list[i];
-    if (tid == 0) p.counts[int64_t(s) * p.Q + q] = int32_t(n);
-    __syncthreads();
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = list[i];
+    if (lane == 0) p.counts[int64_t(s) * p.Q + q] = int32_t(n);
+    __syncwarp();
   }
 }
 
 __global__ void build_blockptr_kernel(const int64_t* __restrict__ post_indptr, const int32_t* __restrict__ post_doc,
-                                      int64_t V, int nblk, uint32_t* __restrict__ blockptr) {
+                                      int64_t V, int nblk, int block_docs, uint32_t* __restrict__ blockptr) {
   const int64_t total = V * int64_t(nblk + 1);
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
     const int64_t t = e / (nblk + 1);
     const int b = int(e % (nblk + 1));
     const int64_t lo0 = post_indptr[t], hi0 = post_indptr[t + 1];
-    const int64_t bound = int64_t(b) * SS_BLOCK_DOCS;
+    const int64_t bound = int64_t(b) * block_docs;
     int64_t lo = lo0, hi = hi0;  // first index with doc >= bound
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
@@ -291,30 +341,61 @@ __global__ void build_blockptr_kernel(const int64_t* __restrict__ post_indptr, c
   }
 }
 
+// Documents per accumulator block: 4096 (16 KB of int32 per warp).  LR_SPARSE_BLOCK_DOCS = 2048 | 4096 | 8192 overrides it
+// for sweeps (read once; an index must be searched with the block size it was built with).
+static int ss_block_docs() {
+  static const int bd = [] {
+    const char* e = getenv("LR_SPARSE_BLOCK_DOCS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 2048 || v == 4096 || v == 8192) ? v : 4096;
+  }();
+  return bd;
+}
+
+static int ss_env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+static bool ss_batch4() { static const bool v = ss_env_int("LR_SPARSE_BATCH") == 4; return v; }   // sweeps; default 8
+static bool ss_acc32_only() { static const bool v = ss_env_int("LR_SPARSE_ACC") == 32; return v; }  // A/B; default 16 + fallback
+
 struct SSPlan {
-  int nblk, S, cap, grid;
-  size_t smem, off_counts, off_cand, total_bytes;
+  int bd, nblk, S, cap;
+  int warps[2], warp_bytes[2];  // [0] = 16-bit accumulators, [1] = int32 accumulators
+  int grid[2];
+  size_t smem[2], off_counts, off_floor, off_cand, total_bytes;
 };
 
 static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   SSPlan pl{};
-  pl.nblk = int((N + SS_BLOCK_DOCS - 1) / SS_BLOCK_DOCS);
-  int cap = 2 * k > k + 256 ? 2 * k : k + 256;
-  pl.cap = (cap + 63) / 64 * 64;
-  pl.smem = size_t(SS_BLOCK_DOCS) * 4 + size_t(pl.cap) * 16 + SS_TERM_CHUNK * (8 + 4 + 4) + SS_TOUCH_CAP * 2;
+  pl.bd = ss_block_docs();
+  pl.nblk = int((N + pl.bd - 1) / pl.bd);
+  int cap = k + (k / 2 > 156 ? k / 2 : 156);  // k = 100 -> 256
+  pl.cap = (cap + 31) / 32 * 32;
   const int G = sm_count();
-  const int ctas_per_sm = int((size_t(227) * 1024) / (pl.smem + 2048));
-  const int slots = G * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
-  // enough units to fill the machine a few times over, at most one unit per document block
-  int64_t S = (int64_t(4) * slots + Q - 1) / Q;
+  for (int m = 0; m < 2; ++m) {
+    pl.warp_bytes[m] = pl.bd * (m ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2;
+    const int warps = int((size_t(227) * 1024 - 1024) / size_t(pl.warp_bytes[m]));
+    pl.warps[m] = warps > SS_MAX_WARPS ? SS_MAX_WARPS : warps;
+    pl.smem[m] = size_t(pl.warps[m]) * pl.warp_bytes[m];
+  }
+  const int64_t slots = int64_t(G) * pl.warps[ss_acc32_only() ? 1 : 0];
+  // enough units to balance the dynamic hand-out (8 per warp), at most one unit per document block and at most 64
+  // lists per query for the merge
+  int64_t S = (8 * slots + Q - 1) / Q;
+  if (S > 64) S = 64;
   if (S > pl.nblk) S = pl.nblk;
   if (S < 1) S = 1;
   pl.S = int(S);
   const int64_t units = Q * S;
-  pl.grid = int(units < slots ? units : slots);
+  for (int m = 0; m < 2; ++m) {
+    const int64_t ctas = (units + pl.warps[m] - 1) / (pl.warps[m] > 0 ? pl.warps[m] : 1);
+    pl.grid[m] = int(ctas < G ? ctas : G);
+  }
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   pl.off_counts = 0;
-  pl.off_cand = align(size_t(pl.S) * Q * 4);
+  pl.off_floor = align(size_t(pl.S) * Q * 4);
+  pl.off_cand = align(pl.off_floor + 2 * size_t(Q) * 4 + 256);  // 2 x floor_q [Q], 2 unit counters, the overflow flag
   pl.total_bytes = align(pl.off_cand + size_t(pl.S) * Q * pl.cap * 8);
   return pl;
 }
@@ -323,17 +404,18 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
 
 using namespace lr;
 
-extern "C" int lr_sparse_block_docs(void) { return SS_BLOCK_DOCS; }
+extern "C" int lr_sparse_block_docs(void) { return ss_block_docs(); }
 
 extern "C" int lr_sparse_build_blockptr(const int64_t* post_indptr, const int32_t* post_doc, int64_t V, int64_t N,
                                         uint32_t* blockptr, void* stream) {
   LR_CHECK_ARG(post_indptr && blockptr && V >= 1 && N >= 1, "build_blockptr: bad arguments");
-  const int nblk = int((N + SS_BLOCK_DOCS - 1) / SS_BLOCK_DOCS);
+  const int bd = ss_block_docs();
+  const int nblk = int((N + bd - 1) / bd);
   const int64_t total = V * int64_t(nblk + 1);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   build_blockptr_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(post_indptr, post_doc, V, nblk,
-                                                                                        blockptr);
+                                                                                        bd, blockptr);
   LR_LAUNCH_CHECK();
   return LR_OK;
 }
@@ -341,6 +423,29 @@ extern "C" int lr_sparse_build_blockptr(const int64_t* post_indptr, const int32_
 extern "C" size_t lr_sparse_score_workspace_bytes(int64_t Q, int64_t N, int k) {
   if (Q < 1 || N < 1 || k < 1) return 0;
   return ss_plan(Q, N, k).total_bytes;
+}
+
+template <int BD, int NB, typename AccT>
+static int ss_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  const int m = sizeof(AccT) == 4 ? 1 : 0;
+  cudaError_t e = cudaFuncSetAttribute(sparse_score_kernel<BD, NB, AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(pl.smem[m]));
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", pl.smem[m], cudaGetErrorString(e));
+    return LR_ECUDA;
+  }
+  sparse_score_kernel<BD, NB, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
+}
+
+template <typename AccT>
+static int ss_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  switch (pl.bd) {
+    case 2048: return ss_launch<2048, 4, AccT>(p, pl, st);
+    case 8192: return ss_launch<8192, 8, AccT>(p, pl, st);
+    default: return ss_batch4() ? ss_launch<4096, 4, AccT>(p, pl, st) : ss_launch<4096, 8, AccT>(p, pl, st);
+  }
 }
 
 extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_tok, const int32_t* q_cnt, int64_t Q,
@@ -355,6 +460,8 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   LR_CHECK_ARG(id_offset >= 0 && id_offset + N <= (int64_t(1) << 32) - 2, "sparse_score: id_offset + N must stay below 2^32");
   LR_CHECK_ARG(out_scores || out_ids || out_keys, "sparse_score: no output requested");
   SSPlan pl = ss_plan(Q, N, k);
+  LR_CHECK_ARG(Q * int64_t(pl.S) < (int64_t(1) << 31), "sparse_score: too many (query, block range) units");
+  LR_CHECK_ARG(pl.warps[0] >= 1 && pl.warps[1] >= 1, "sparse_score: k (%d) leaves no shared memory for a worker", k);
   if (!workspace || ws_bytes < pl.total_bytes || (uintptr_t(workspace) & 255)) {
     set_error("sparse_score: workspace too small or misaligned (%zu given, %zu needed)", ws_bytes, pl.total_bytes);
     return LR_EWORKSPACE;
@@ -367,13 +474,25 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   p.V = V; p.N = N; p.nblk = pl.nblk; p.S = pl.S; p.k = k; p.cap = pl.cap;
   p.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   p.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
-  cudaError_t e = cudaFuncSetAttribute(sparse_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem));
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", pl.smem, cudaGetErrorString(e));
-    return LR_ECUDA;
+  uint32_t* ctl = reinterpret_cast<uint32_t*>(ws + pl.off_floor);  // floor16 [Q] | floor32 [Q] | next16 | next32 | overflow
+  LR_CUDA(cudaMemsetAsync(ctl, 0, 2 * size_t(Q) * 4 + 12, st));
+  p.overflow = ctl + 2 * Q + 2;
+  int rc = LR_OK;
+  if (!ss_acc32_only()) {
+    // optimistic pass with 16-bit accumulators (exact unless a document's score would exceed 65535: flag -> pass 2)
+    p.floor_q = ctl;
+    p.next_unit = ctl + 2 * Q;
+    p.warp_bytes = pl.warp_bytes[0];
+    rc = ss_dispatch<uint16_t>(p, pl, st);
+    if (rc != LR_OK) return rc;
+  } else {
+    p.overflow = nullptr;
   }
-  sparse_score_kernel<<<pl.grid, SS_THREADS, pl.smem, st>>>(p);
-  LR_LAUNCH_CHECK();
+  p.floor_q = ctl + Q;
+  p.next_unit = ctl + 2 * Q + 1;
+  p.warp_bytes = pl.warp_bytes[1];
+  rc = ss_dispatch<int32_t>(p, pl, st);  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
+  if (rc != LR_OK) return rc;
   return lr_topk_merge(p.cand, p.counts, pl.S, Q, Q, pl.cap, k, LR_SCORE_U32, id_offset, out_scores, out_ids, out_keys,
                        stream);
 }

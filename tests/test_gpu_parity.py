@@ -367,6 +367,51 @@ def test_sparse_score_bit_exact(N, V, nnz, Q, k):
         searcher.retrieve_with_emb(queries, ["q"] * Q, k)
 
 
+def test_sparse_score_long_queries_and_dense_blocks():
+    """Queries with more than 32 distinct terms (several term chunks per step), a head term present in most documents
+    (touched-list overflow -> block scan) and k close to the list capacity; counts <= 0 contribute nothing."""
+    rng = np.random.default_rng(77)
+    N, V, k = 30000, 400, 300
+    docs = _rand_docs(rng, N, V, 24)
+    for j in range(0, N, 3):
+        docs[j]["7"] = int(rng.integers(1, 50))  # head term
+    searcher = lr.ImpactSearch(vocab_size=V)
+    searcher.index(docs, [f"d{j}" for j in range(N)])
+    queries = [" ".join(str(int(t)) for t in rng.integers(0, V, size=n)) for n in (33, 64, 100, 257, 1, 31, 32)]
+    queries.append("7 7 7 8")
+    from lightretriever_b200.sparse_search import parse_queries
+    qd = [oracle.query_counts([int(t) for t in s.split()]) for s in queries]
+    es, ei = oracle.impact_topk(qd, [{int(a): b for a, b in d.items()} for d in docs], k)
+    s, i = searcher._ensure_index().search_device(*parse_queries(queries, V), k)
+    np.testing.assert_array_equal(_np(i), ei)
+    np.testing.assert_array_equal(_np(s), es)
+    # a zero / negative count removes the term
+    qi, qt, qc = parse_queries(["7 8 9", "7 9"], V)
+    qc = np.asarray(qc).copy()
+    qt_l = list(np.asarray(qt)[: int(np.asarray(qi)[1])])
+    qc[qt_l.index(8)] = 0
+    s2, i2 = searcher._ensure_index().search_device(qi, qt, qc, 20)
+    np.testing.assert_array_equal(_np(i2)[0], _np(i2)[1])
+    np.testing.assert_array_equal(_np(s2)[0], _np(s2)[1])
+
+
+def test_sparse_score_wide_scores_take_the_int32_pass():
+    """Scores above 65535 do not fit the 16-bit accumulators of the first pass: the overflow flag must route the launch
+    through the int32 pass, bit-exact; a second search on the same index (small scores) stays on the 16-bit pass."""
+    rng = np.random.default_rng(5)
+    N, V, k = 20000, 120, 50
+    docs = _rand_docs(rng, N, V, 20, max_imp=65535)
+    searcher = lr.ImpactSearch(vocab_size=V)
+    searcher.index(docs, [f"d{j}" for j in range(N)])
+    from lightretriever_b200.sparse_search import parse_queries
+    for queries in (["3 3 3 4 5 6 7", "8 9 10 11 12 13 14 15 16 17 18 19 20 21 22", "30"] * 5, ["40", "41 42"]):
+        qd = [oracle.query_counts([int(t) for t in s.split()]) for s in queries]
+        es, ei = oracle.impact_topk(qd, [{int(a): b for a, b in d.items()} for d in docs], k)
+        s, i = searcher._ensure_index().search_device(*parse_queries(queries, V), k)
+        np.testing.assert_array_equal(_np(i), ei)
+        np.testing.assert_array_equal(_np(s), es)
+
+
 def test_sparse_head_to_sparse_search_roundtrip():
     """K3 output (CSR) feeds K4 directly, and through the reference's JSON form, with identical results."""
     gen = torch.Generator().manual_seed(9)

@@ -37,7 +37,7 @@ def test_workspace_sizing_needs_no_gpu():
     assert 0 < ws < (16 << 30)
     assert lib.lr_flatip_workspace_bytes(10000, 8_800_000, 1000) > ws
     assert lib.lr_sparse_score_workspace_bytes(32, 8_800_000, 100) > 0
-    assert lib.lr_sparse_block_docs() == 16384
+    assert lib.lr_sparse_block_docs() in (2048, 4096, 8192)
     assert lib.lr_flatip_workspace_bytes(0, 10, 10) == 0
 
 
