@@ -23,11 +23,20 @@ struct PassPlan {
   int tile_begin, tile_end, splits, units, grid, rounds;
   int sched, band_size, n_bands;  // sched 1: fixed teams per band (band_size groups per full band)
 };
+constexpr int MAX_MID = 6;
 struct FlatipPlan {
   int cl, pair, m_groups, m_tiles, n_tiles, band_size, n_bands, cap, n_clusters;
   int64_t q_pad;
   PassPlan main, prefix;  // prefix.units == 0 -> single phase
-  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, off_teamctr, total_bytes;
+  // Epilogue-bound searches (short rows, d_used <= 1024) refresh the thresholds more than once: passes over geometrically
+  // growing tile ranges between the prefix and the main pass, each followed by a merge that re-seeds every query's
+  // threshold with its k-th best score so far.
+  int n_mid;
+  PassPlan mid[MAX_MID];
+  int wide;  // two epilogue warp sets (umma_gemm.cuh WIDE): every split owns TWO candidate lists
+  int lmul;  // candidate lists per split (1 or 2)
+  int max_lists;  // lists of the widest pass + 1 (the carried top-k)
+  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, off_carry, off_teamctr, total_bytes;
 };
 
 // Team schedule of the main pass: bands of g row groups; inside a band the clusters form floor(nc / g) fixed teams, each
@@ -104,7 +113,7 @@ static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile
   return pp;
 }
 
-static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
+static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
   FlatipPlan pl{};
   // Candidate-list capacity.  The running threshold of a row only rises when its list is cut back to the top-k, so
   // between two cuts exactly cap-k entries are admitted and the number of documents consumed grows by cap/k per cut;
@@ -130,7 +139,11 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;
   pl.n_tiles = int((N + BN - 1) / BN);
   pl.q_pad = int64_t(pl.m_tiles) * BM;
-  const int64_t list_bytes = pl.q_pad * int64_t(pl.cap) * 8;
+  // Short rows (MRL prefixes): a 128x256 tile needs d_used/16 MMAs of 128 cycles but ~4-5k cycles of one epilogue warp
+  // per TMEM lane quarter, so below ~768 columns the epilogue sets the pace: run two epilogue sets on alternate tiles.
+  pl.wide = env_int("LR_FLATIP_WIDE", (d_used <= 768 && Q > BM && !long_lists) ? 1 : 0) != 0 && !long_lists;
+  pl.lmul = pl.wide ? 2 : 1;
+  const int64_t list_bytes = pl.q_pad * int64_t(pl.cap) * 8 * pl.lmul;
   const int64_t s_cap = (int64_t(12) << 30) / (list_bytes > 0 ? list_bytes : 1);
 
   // Phase A (warm start) when the search is compute-bound and long enough to amortise it.  Measured on the 1.1M x 4096
@@ -161,7 +174,26 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   }
   if (prefix_tiles > 0)
     pl.prefix = plan_pass(pl.m_groups, geo.n_clusters, 0, prefix_tiles, s_cap, prefix_splits_forced);
-  pl.main = plan_pass(pl.m_groups, geo.n_clusters, prefix_tiles, pl.n_tiles, s_cap, env_int("LR_FLATIP_SPLITS", 0));
+  // Threshold refreshes for epilogue-bound searches: with d_used <= 1024 a tile's MMAs are shorter than its epilogue,
+  // so every candidate appended under a stale threshold costs wall time.  Measured at 10k x 1.1M (profiles/): the lists
+  // of a single main pass take k*N/prefix = 3.4k candidates per query; ranges growing 4x per pass bring that below 1k.
+  int main_begin = prefix_tiles;
+  pl.n_mid = 0;
+  const int refresh = env_int("LR_FLATIP_REFRESH", d_used <= 1024 ? 1 : 0);
+  if (refresh && prefix_tiles >= 128 && prefix_tiles == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN)) {
+    int growth = env_int("LR_FLATIP_REFRESH_GROWTH", 4);
+    if (growth < 2) growth = 2;
+    int64_t len = int64_t(prefix_tiles) * (growth - 1);
+    while (pl.n_mid < MAX_MID && main_begin + len + len < pl.n_tiles) {
+      pl.mid[pl.n_mid] = plan_pass(pl.m_groups, geo.n_clusters, main_begin, main_begin + int(len), s_cap, 0);
+      pl.mid[pl.n_mid].band_size = pl.band_size;
+      pl.mid[pl.n_mid].n_bands = pl.n_bands;
+      ++pl.n_mid;
+      main_begin += int(len);
+      len *= growth;
+    }
+  }
+  pl.main = plan_pass(pl.m_groups, geo.n_clusters, main_begin, pl.n_tiles, s_cap, env_int("LR_FLATIP_SPLITS", 0));
   pl.main.band_size = pl.band_size;
   pl.main.n_bands = pl.n_bands;
   pl.prefix.band_size = pl.band_size;
@@ -169,17 +201,21 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k) {
   // Large batches: fixed teams (see plan_teams).  LR_FLATIP_SCHED=0 keeps the round-robin schedule.
   if (env_int("LR_FLATIP_SCHED", 1) != 0 && pl.cl == 2 && pl.m_groups >= 8 && env_int("LR_FLATIP_SPLITS", 0) == 0) {
     PassPlan tp = pl.main;
-    if (plan_teams(pl.m_groups, geo.n_clusters, pl.n_tiles - prefix_tiles, s_cap, tp)) pl.main = tp;
+    if (plan_teams(pl.m_groups, geo.n_clusters, pl.n_tiles - main_begin, s_cap, tp)) pl.main = tp;
   }
 
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
-  const int main_lists = pl.main.splits + (prefix_tiles > 0 ? 1 : 0);  // + the prefix's merged top-k
+  int main_lists = pl.main.splits;
+  for (int i = 0; i < pl.n_mid; ++i) main_lists = pl.mid[i].splits > main_lists ? pl.mid[i].splits : main_lists;
+  main_lists = main_lists * pl.lmul + (prefix_tiles > 0 ? 1 : 0);  // + the carried top-k of the earlier passes
+  pl.max_lists = main_lists;
   pl.off_gthr = 0;
   pl.off_counts = align(size_t(pl.q_pad) * 4);
   pl.off_cand = align(pl.off_counts + size_t(main_lists) * pl.q_pad * 4);
   pl.off_pcounts = align(pl.off_cand + size_t(main_lists) * pl.q_pad * pl.cap * 8);
-  pl.off_pcand = align(pl.off_pcounts + size_t(pl.prefix.splits) * pl.q_pad * 4);
-  pl.off_teamctr = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.q_pad * pl.cap * 8);
+  pl.off_pcand = align(pl.off_pcounts + size_t(pl.prefix.splits) * pl.lmul * pl.q_pad * 4);
+  pl.off_carry = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.lmul * pl.q_pad * pl.cap * 8);
+  pl.off_teamctr = align(pl.off_carry + (prefix_tiles > 0 ? size_t(pl.q_pad) * pl.cap * 8 : 0));
   pl.total_bytes = align(pl.off_teamctr + size_t(pl.main.n_bands) * size_t(pl.n_clusters) * 4 + 256);
   return pl;
 }
@@ -208,7 +244,10 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
   prm.band_size = pp.band_size ? pp.band_size : pl.band_size;  // plan_pass leaves the band layout to the geometry
   prm.n_bands = pp.band_size ? pp.n_bands : pl.n_bands; prm.units = pp.units;
   prm.sched = pp.sched;
-  prm.team_window = env_int("LR_FLATIP_TEAM_WINDOW", 1);
+  // The window is worth one full-width tile of operand traffic (64 k-blocks): with MRL prefixes (2..16 k-blocks per tile)
+  // a one-tile window would make the team counter round trip — not the MMA — the pace of the kernel.
+  const int auto_window = prm.kblocks >= 64 ? 1 : (64 + prm.kblocks - 1) / prm.kblocks;
+  prm.team_window = env_int("LR_FLATIP_TEAM_WINDOW", auto_window);
   prm.policy_a = l2_policy(env_int("LR_FLATIP_POLICY_A", 0));
   prm.policy_b = l2_policy(env_int("LR_FLATIP_POLICY_B", 0));
   prm.debug_flags = env_int("LR_FLATIP_DEBUG", 0);
@@ -230,24 +269,35 @@ static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorM
     return pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2, false, true>(tmA, tmB, prm, pp.grid * 2, st)
                       : launch_umma_gemm<EPI_TOPK, 1, false, true>(tmA, tmB, prm, pp.grid, st);
   }
+  if (EPI == EPI_TOPK && pl.wide) {
+    if (pl.pair) return launch_umma_gemm<EPI_TOPK, 2, true, false, true>(tmA, tmB, prm, pp.grid * 2, st);
+    return pl.cl == 2 ? launch_umma_gemm<EPI_TOPK, 2, false, false, true>(tmA, tmB, prm, pp.grid * 2, st)
+                      : launch_umma_gemm<EPI_TOPK, 1, false, false, true>(tmA, tmB, prm, pp.grid, st);
+  }
   if (pl.pair) return launch_umma_gemm<EPI, 2, true>(tmA, tmB, prm, pp.grid * 2, st);
   return pl.cl == 2 ? launch_umma_gemm<EPI, 2>(tmA, tmB, prm, pp.grid * 2, st)
                     : launch_umma_gemm<EPI, 1>(tmA, tmB, prm, pp.grid, st);
 }
 
-// gthr[q] = score key of the prefix's k-th best document (0 when the prefix holds fewer than k documents);
-// counts of the extra merge list = k
-__global__ void seed_threshold_kernel(const uint64_t* __restrict__ prefix_keys, int64_t key_stride, int k, int64_t q_pad,
-                                      int64_t Q, uint32_t* __restrict__ gthr, int32_t* __restrict__ counts) {
-  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+// Carries the merged top-k of the passes so far into the next pass: copies the k keys of every query into that pass's
+// extra candidate list (counts = k), and seeds gthr[q] with the score key of the k-th best (0 when fewer than k
+// documents have been seen — any k documents give a valid lower bound of the final k-th score).
+__global__ void carry_topk_kernel(const uint64_t* __restrict__ merged, int64_t key_stride, int k, int64_t q_pad,
+                                  int64_t Q, uint64_t* __restrict__ dst, uint32_t* __restrict__ gthr,
+                                  int32_t* __restrict__ counts) {
+  const int64_t q = blockIdx.x;
   if (q >= q_pad) return;
-  uint32_t g = 0;
-  if (q < Q) {
-    const uint64_t kth = prefix_keys[q * key_stride + (k - 1)];
-    if (kth != 0ull) g = key_hi(kth);
+  if (q < Q)
+    for (int i = threadIdx.x; i < k; i += blockDim.x) dst[q * key_stride + i] = merged[q * key_stride + i];
+  if (threadIdx.x == 0) {
+    uint32_t g = 0;
+    if (q < Q) {
+      const uint64_t kth = merged[q * key_stride + (k - 1)];
+      if (kth != 0ull) g = key_hi(kth);
+    }
+    gthr[q] = g;
+    counts[q] = q < Q ? k : 0;
   }
-  gthr[q] = g;
-  counts[q] = q < Q ? k : 0;
 }
 
 }  // namespace lr
@@ -256,7 +306,7 @@ using namespace lr;
 
 extern "C" size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k) {
   if (Q < 1 || N < 1 || k < 1) return 0;
-  return make_plan(Q, N, k).total_bytes;
+  return make_plan(Q, N, k, 4096).total_bytes >= make_plan(Q, N, k, 64).total_bytes ? make_plan(Q, N, k, 4096).total_bytes : make_plan(Q, N, k, 64).total_bytes;
 }
 
 // Plan of a (Q, N, k) search without running it (no device needed beyond the SM count): for tests and capacity planning.
@@ -265,7 +315,7 @@ extern "C" size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k) {
 // out[11]=main grid (CTAs) out[12]=band (row tiles) out[13]=workspace bytes out[14]=main rounds out[15]=n_clusters
 extern "C" int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16) {
   LR_CHECK_ARG(out16 && Q >= 1 && N >= 1 && k >= 1 && k <= 2048, "flatip_plan: bad arguments");
-  const FlatipPlan pl = make_plan(Q, N, k);
+  const FlatipPlan pl = make_plan(Q, N, k, 4096);
   out16[0] = pl.cl; out16[1] = pl.pair; out16[2] = pl.m_tiles; out16[3] = pl.n_tiles; out16[4] = pl.cap;
   out16[5] = pl.prefix.tile_end; out16[6] = pl.prefix.splits; out16[7] = pl.prefix.units;
   out16[8] = pl.main.tile_begin; out16[9] = pl.main.splits; out16[10] = pl.main.units;
@@ -290,7 +340,7 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   LR_CHECK_ARG(k >= 1 && k <= 2048, "flatip: k (%d) must be in [1, 2048]", k);
   LR_CHECK_ARG(id_offset >= 0 && id_offset + N <= (int64_t(1) << 32) - 2, "flatip: id_offset + N must stay below 2^32");
   LR_CHECK_ARG(out_scores || out_ids || out_keys, "flatip: no output requested");
-  FlatipPlan pl = make_plan(Q, N, k);
+  FlatipPlan pl = make_plan(Q, N, k, d_used);
   if (!workspace || ws_bytes < pl.total_bytes || (uintptr_t(workspace) & 255)) {
     set_error("flatip: workspace too small or misaligned (%zu given, %zu needed, 256-byte aligned)", ws_bytes,
               pl.total_bytes);
@@ -313,37 +363,54 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   prm.q_scale = q_scale; prm.c_scale = c_scale;
   prm.gthr = gthr;
   const ProfileEvents pe_saved = profile_events();
+  uint64_t* carry = reinterpret_cast<uint64_t*>(ws + pl.off_carry);  // merged top-k so far: [q_pad][cap], k used
+  auto run_pass = [&](const PassPlan& pp, bool last) -> int {
+    // carried top-k -> list slot `pp.splits` of the candidate array (+ thresholds), the pass, then the merge
+    const int own_lists = pp.splits * pl.lmul;
+    uint64_t* slot = cand + size_t(own_lists) * pl.q_pad * pl.cap;
+    if (two_phase) {
+      carry_topk_kernel<<<unsigned(pl.q_pad), 128, 0, st>>>(carry, pl.cap, k, pl.q_pad, Q, slot, gthr,
+                                                            counts + size_t(own_lists) * pl.q_pad);
+      LR_LAUNCH_CHECK();
+    }
+    fill_params(prm, pl, pp, Q, N, d_used);
+    if (pp.sched) {
+      prm.team_ctr = reinterpret_cast<uint32_t*>(ws + pl.off_teamctr);
+      LR_CUDA(cudaMemsetAsync(prm.team_ctr, 0, size_t(pp.n_bands) * size_t(pl.n_clusters) * 4, st));
+    }
+    prm.counts = counts;
+    prm.cand = cand;
+    if (!last) profile_events() = ProfileEvents{};  // the profiling events bracket the main pass only
+    int r = launch_pass<EPI_TOPK>(pl, pp, tmA, tmB, prm, st);
+    profile_events() = pe_saved;
+    if (r) return r;
+    const int lists = own_lists + (two_phase ? 1 : 0);
+    if (last)
+      return topk_merge_strided(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, id_offset, out_scores, out_ids,
+                                out_keys, k, st);
+    return topk_merge_strided(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0, nullptr, nullptr, carry,
+                              pl.cap, st);
+  };
   if (two_phase) {
-    // ---- phase A: prefix -> its top-k lands in list slot `main.splits` of the main candidate array
-    profile_events() = ProfileEvents{};  // the profiling events bracket the main pass only
+    // ---- phase A: prefix -> merged top-k in `carry`
+    profile_events() = ProfileEvents{};
     fill_params(prm, pl, pl.prefix, Q, N, d_used);
     prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_pcounts);
     prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_pcand);
     LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
     rc = launch_pass<EPI_TOPK>(pl, pl.prefix, tmA, tmB, prm, st);
-    uint64_t* slot = cand + size_t(pl.main.splits) * pl.q_pad * pl.cap;
     if (!rc)
-      rc = topk_merge_strided(prm.cand, prm.counts, pl.prefix.splits, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0, nullptr,
-                              nullptr, slot, pl.cap, st);
+      rc = topk_merge_strided(prm.cand, prm.counts, pl.prefix.splits * pl.lmul, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0,
+                              nullptr, nullptr, carry, pl.cap, st);
     profile_events() = pe_saved;
     if (rc) return rc;
-    seed_threshold_kernel<<<unsigned((pl.q_pad + 255) / 256), 256, 0, st>>>(
-        slot, pl.cap, k, pl.q_pad, Q, gthr, counts + size_t(pl.main.splits) * pl.q_pad);
-    LR_LAUNCH_CHECK();
   } else if (!(debug & 2)) {  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)
     LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
   }
-  // ---- phase B / single phase
-  fill_params(prm, pl, pl.main, Q, N, d_used);
-  if (pl.main.sched) {
-    prm.team_ctr = reinterpret_cast<uint32_t*>(ws + pl.off_teamctr);
-    LR_CUDA(cudaMemsetAsync(prm.team_ctr, 0, size_t(pl.main.n_bands) * size_t(pl.n_clusters) * 4, st));
-  }
-  prm.counts = counts;
-  prm.cand = cand;
-  if ((rc = launch_pass<EPI_TOPK>(pl, pl.main, tmA, tmB, prm, st))) return rc;
-  return topk_merge_strided(cand, counts, pl.main.splits + (two_phase ? 1 : 0), Q, pl.q_pad, pl.cap, k, LR_SCORE_F32,
-                            id_offset, out_scores, out_ids, out_keys, k, st);
+  // ---- threshold-refresh passes (epilogue-bound searches only), then phase B / single phase
+  for (int i = 0; i < pl.n_mid; ++i)
+    if ((rc = run_pass(pl.mid[i], false))) return rc;
+  return run_pass(pl.main, true);
 }
 
 extern "C" int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,
@@ -351,7 +418,7 @@ extern "C" int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, 
   int rc = check_flatip_args(q, ldq, corpus, ldc, Q, N, d_used);
   if (rc) return rc;
   LR_CHECK_ARG(out_scores, "flatip_scores: null output");
-  FlatipPlan pl = make_plan(Q, N, 1);
+  FlatipPlan pl = make_plan(Q, N, 1, 4096);
   const PassPlan all = plan_pass(pl.m_groups, pl.n_clusters, 0, pl.n_tiles, 1 << 20, 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;

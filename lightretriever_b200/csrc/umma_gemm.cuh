@@ -41,21 +41,30 @@ constexpr int PIPE_BYTES = 4 * (A_BYTES + B_BYTES);  // shared memory of the ope
 // cta_group::2 (CTA pair, one M=256 MMA): a stage holds A (16 KB) + this CTA's HALF of B (16 KB): 6 stages.
 // BIGLIST (top-k with long candidate lists, k > 352): one 48 KB stage (two 32 KB stages for a pair) is given to the
 // epilogue warps' list-staging area instead, so that lists of up to 2304 (2816) entries are still cut in shared memory.
-template <bool PAIR, bool BIGLIST> struct PipeCfg {
+// WIDE (top-k with short rows, d_used <= 768, where a tile's epilogue outlasts its MMAs): EIGHT epilogue warps in two
+// sets that take alternate tiles (set = accumulator buffer), each with its own candidate lists; one ring stage is given
+// to the second set's histograms, column scales and list staging.
+template <bool PAIR, bool BIGLIST, bool WIDE = false> struct PipeCfg {
+  static_assert(!(BIGLIST && WIDE), "WIDE is for short lists");
   static constexpr int kBBytes = PAIR ? B_BYTES / 2 : B_BYTES;
   static constexpr int kStageBytes = A_BYTES + kBBytes;
-  static constexpr int kStages = PIPE_BYTES / kStageBytes - (BIGLIST ? (PAIR ? 2 : 1) : 0);
+  static constexpr int kStages = PIPE_BYTES / kStageBytes - (BIGLIST ? (PAIR ? 2 : 1) : 0) - (WIDE ? 1 : 0);
   static constexpr int kPipeBytes = kStages * kStageBytes;
 };
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS_WIDE = 320;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STAGES = 2;
 constexpr int SMEM_BAR_BYTES = 256;
 constexpr int SMEM_HIST_BYTES = 4 * 256 * 4;
 constexpr int LIST_STAGE_ENTRIES = 768;  // per epilogue warp: a candidate list of <= 768 entries is compacted in smem
 constexpr int SMEM_LIST_BYTES = 4 * LIST_STAGE_ENTRIES * 8;
-template <bool PAIR, bool BIGLIST> struct ListCfg {
-  static constexpr int kEntries = LIST_STAGE_ENTRIES + (PIPE_BYTES - PipeCfg<PAIR, BIGLIST>::kPipeBytes) / (4 * 8);
+template <bool PAIR, bool BIGLIST, bool WIDE = false> struct ListCfg {
+  static constexpr int kWarps = WIDE ? 8 : 4;  // epilogue warps
+  // what the ring left, minus the second set's histograms and column scales
+  static constexpr int kListBytes = SMEM_LIST_BYTES + (PIPE_BYTES - PipeCfg<PAIR, BIGLIST, WIDE>::kPipeBytes) -
+                                    (WIDE ? SMEM_HIST_BYTES + 4 * 256 * 4 : 0);
+  static constexpr int kEntries = kListBytes / (kWarps * 8);
 };
 constexpr int SMEM_CS_BYTES = 4 * BN * 4;  // per epilogue warp: the column scales of the current tile
 constexpr int GEMM_SMEM_TOTAL =
@@ -230,15 +239,17 @@ constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfl
 // PAIR (requires CL == 2): the two CTAs form one cta_group::2 MMA — M = 256 (128 rows per CTA), each CTA stores its A
 // tile and HALF of B (the tensor cores read both halves), the leader CTA's thread issues the MMAs for both, TMA
 // completions of both CTAs are counted on the leader's full barrier, commits are multicast to both CTAs.
-template <int EPI, int CL, bool PAIR, bool BIGLIST>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int EPI, int CL, bool PAIR, bool BIGLIST, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? GEMM_THREADS_WIDE : GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   static_assert(!PAIR || CL == 2, "cta_group::2 needs a cluster of two CTAs");
-  constexpr int STAGES = PipeCfg<PAIR, BIGLIST>::kStages;
-  constexpr int STAGE_BYTES = PipeCfg<PAIR, BIGLIST>::kStageBytes;
-  constexpr int kPipe = PipeCfg<PAIR, BIGLIST>::kPipeBytes;
-  constexpr int kListEntries = ListCfg<PAIR, BIGLIST>::kEntries;
+  static_assert(!WIDE || EPI == EPI_TOPK, "the two-set epilogue exists for the top-k epilogue only");
+  constexpr int STAGES = PipeCfg<PAIR, BIGLIST, WIDE>::kStages;
+  constexpr int STAGE_BYTES = PipeCfg<PAIR, BIGLIST, WIDE>::kStageBytes;
+  constexpr int kPipe = PipeCfg<PAIR, BIGLIST, WIDE>::kPipeBytes;
+  constexpr int kListEntries = ListCfg<PAIR, BIGLIST, WIDE>::kEntries;
+  constexpr int NEPI = ListCfg<PAIR, BIGLIST, WIDE>::kWarps;
   // shared memory map: operand ring | barriers | histograms | column scales | list staging (takes what the ring left)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -253,9 +264,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + kPipe + 8 * (2 * STAGES + 2 * ACC_STAGES));
   uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem_gen + kPipe + SMEM_BAR_BYTES);
-  float* cs_all = reinterpret_cast<float*>(smem_gen + kPipe + SMEM_BAR_BYTES + SMEM_HIST_BYTES);
+  float* cs_all = reinterpret_cast<float*>(smem_gen + kPipe + SMEM_BAR_BYTES + NEPI * 256 * 4);
   uint64_t* list_stage_all =
-      reinterpret_cast<uint64_t*>(smem_gen + kPipe + SMEM_BAR_BYTES + SMEM_HIST_BYTES + SMEM_CS_BYTES);
+      reinterpret_cast<uint64_t*>(smem_gen + kPipe + SMEM_BAR_BYTES + NEPI * 256 * 4 + NEPI * BN * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -419,17 +430,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
+    const int eset = WIDE ? (warp - 2) >> 2 : 0;  // WIDE: set 0 drains accumulator buffer 0 (even tiles), set 1 buffer 1
     uint32_t* hist = hist_all + (warp - 2) * 256;
     uint64_t* list_stage = list_stage_all + (warp - 2) * kListEntries;
     float* cs_smem = cs_all + (warp - 2) * BN;
+    int64_t tiles_before = 0;  // tiles of the earlier units of this cluster: the accumulator buffers alternate globally
     const bool has_scale = (EPI == EPI_TOPK) && (p.q_scale != nullptr || p.c_scale != nullptr);
     const uint32_t full = 0xFFFFFFFFu;
-    int acc = 0;
+    int acc = WIDE ? eset : 0;
     uint32_t acc_phase = 0;
     for_each_unit(p, cluster_id, n_clusters, [&](int m_group, int split, int, int) {
       int64_t c0, c1;
       const int m_tile = m_group * CL + cta_rank;
       split_cols<EPI>(p, split, c0, c1);
+      const int list_idx = WIDE ? split * 2 + eset : split;  // candidate list of this (unit, epilogue set)
+      constexpr int64_t TILE_STEP = WIDE ? 2 * BN : BN;
+      // first tile of the unit that this set owns
+      const int64_t cfirst = c0 + ((WIDE && int(tiles_before & 1) != eset) ? BN : 0);
+      tiles_before += (c1 - c0 + BN - 1) / BN;
       const int64_t row = int64_t(m_tile) * BM + row_in_tile;
       const bool row_valid = row < p.rows;
       const bool tile_valid = m_tile < p.m_tiles;  // false only for the padding tile of an odd last group
@@ -443,7 +461,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float bias_v = 0.0f;
       int64_t seg = 0, seg_end = 0;
       if (EPI == EPI_TOPK && tile_valid) {
-        buf = p.cand + (int64_t(split) * p.row_pad + row) * p.cap;
+        buf = p.cand + (int64_t(list_idx) * p.row_pad + row) * p.cap;
         if (row_valid && p.q_scale) qs = p.q_scale[row];
       }
       if (EPI == EPI_MAXTOK) {
@@ -451,24 +469,40 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         seg = c0 / p.seg_len;
         seg_end = c0 + p.seg_len;
       }
-      for (int64_t cb = c0; cb < c1; cb += BN) {
+      // The shared threshold and the column scales of a tile are fetched one tile ahead (a threshold that is one tile
+      // stale is still a valid lower bound), so no global latency sits between two tiles of an epilogue-bound pass.
+      uint32_t g_pref = 0;
+      float cs_pref[BN / 32];
+      auto load_cs = [&](int64_t cbx) {
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          const int64_t dcol = cbx + i * 32 + lane;
+          cs_pref[i] = (p.c_scale && dcol < p.cols) ? p.c_scale[dcol] : (p.c_scale ? 0.0f : 1.0f);
+        }
+      };
+      if (EPI == EPI_TOPK) {
+        if (row_valid) g_pref = ld_relaxed_u32(p.gthr + row);
+        if (has_scale && cfirst < c1) load_cs(cfirst);
+      }
+      for (int64_t cb = cfirst; cb < c1; cb += TILE_STEP) {
         const int n_valid = (c1 - cb < int64_t(BN)) ? int(c1 - cb) : BN;
         float thr = INFINITY;
         if (EPI == EPI_TOPK && row_valid) {
-          const uint32_t g = ld_relaxed_u32(p.gthr + row);
+          const uint32_t g = g_pref;
           const float tg = (g <= KEY_NEG_INF) ? -INFINITY : key_to_f32(g - 1u);  // s >= gthr  <=>  s > tg
           thr = fmaxf(thr_local, tg);
           if (p.debug_flags & 1) thr = INFINITY;
         }
         if (EPI == EPI_TOPK && has_scale) {
-          // column scales of this tile -> shared memory (read back as broadcasts), overlapped with the MMA wait
+          // column scales of this tile -> shared memory (read back as broadcasts)
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) {
-            const int64_t dcol = cb + i * 32 + lane;
-            cs_smem[i * 32 + lane] = (p.c_scale && dcol < p.cols) ? p.c_scale[dcol] : (p.c_scale ? 0.0f : 1.0f);
-          }
+          for (int i = 0; i < BN / 32; ++i) cs_smem[i * 32 + lane] = cs_pref[i];
           __syncwarp();
+        }
+        if (EPI == EPI_TOPK && cb + TILE_STEP < c1) {
+          if (row_valid) g_pref = ld_relaxed_u32(p.gthr + row);
+          if (has_scale) load_cs(cb + TILE_STEP);
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
@@ -478,28 +512,59 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // work), the tcgen05.ld of chunk c+1 is in flight.  A chunk first yields a 32-bit pass mask; the (rare) appends
           // and list cuts run only after the in-flight load has completed.
           const int nchunks = (n_valid + 31) >> 5;
+          // Scaled scores (MRL prefixes): the row scale is folded into the threshold, thr_s = thr / qs nudged down, so the
+          // filter costs one LDS + FFMA + funnel shift per score (sign of thr_s - v * cs[j]); it may admit a score that
+          // is not above the exact threshold, which the append path re-checks with the exact product.
+          float thr_s = thr;
+          if (has_scale && thr < INFINITY && thr > -INFINITY) {
+            thr_s = thr / qs;
+            thr_s -= fabsf(thr_s) * 4.8e-7f + 1e-37f;  // 4 ulp: thr_s * qs <= thr in every rounding
+          }
+          // Pass mask of a chunk from sign bits: d = thr - score is negative exactly when score > thr (thr - s is +0 for
+          // s == thr; thr = +inf rejects and thr = -inf admits everything).  One FADD (FFMA with a column scale) and one
+          // funnel shift per score, in four independent 8-score chains — the epilogue warp is alone on its scheduler, so
+          // dependent chains, not issue slots, set its pace.
           auto pass_mask = [&](const uint32_t (&v)[32], int c) -> uint32_t {
-            uint32_t m = 0;
-            if (has_scale) {
+            uint32_t mq[4] = {0u, 0u, 0u, 0u};
+            if (has_scale) {  // warp-uniform: two straight-line bodies, not per-score predication
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                m |= (__uint_as_float(v[j]) * (qs * cs_smem[c * 32 + j]) > thr) ? (1u << j) : 0u;
+              for (int t = 7; t >= 0; --t) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const int j = qd * 8 + t;
+                  const float dlt = fmaf(-__uint_as_float(v[j]), cs_smem[c * 32 + j], thr_s);
+                  mq[qd] = __funnelshift_l(__float_as_uint(dlt), mq[qd], 1);  // mq = mq << 1 | sign(dlt)
+                }
+              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+              for (int t = 7; t >= 0; --t) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const int j = qd * 8 + t;
+                  const float dlt = thr - __uint_as_float(v[j]);
+                  mq[qd] = __funnelshift_l(__float_as_uint(dlt), mq[qd], 1);
+                }
+              }
             }
+            const uint32_t m = mq[0] | (mq[1] << 8) | (mq[2] << 16) | (mq[3] << 24);
             const int lim = n_valid - c * 32;  // columns >= lim are padding
             return lim >= 32 ? m : (m & ((1u << lim) - 1u));
           };
           auto append_and_cut = [&](const uint32_t (&v)[32], uint32_t m, int c) {
             // Each lane walks its OWN hits (the loop runs max-over-lanes popc(m) times, usually 0..2) and fetches v[j]
-            // with a branch-free 5-level select tree, since registers cannot be indexed dynamically.
+            // with a branch-free 5-level select tree, since registers cannot be indexed dynamically.  (Walking the union
+            // of the lanes' hit columns with a warp-uniform switch was measured 25-75% slower: more iterations, and a
+            // branch tree instead of selects.)
             while (m) {
               const int j = __ffs(m) - 1;
               m &= m - 1;
               const uint32_t x = select32(v, j);
               float sc = __uint_as_float(x);
-              if (has_scale) sc *= (qs * cs_smem[c * 32 + j]);
+              if (has_scale) {
+                sc *= (qs * cs_smem[c * 32 + j]);
+                if (!(sc > thr)) continue;  // the folded filter is conservative: exact re-check
+              }
               st_cg_u64(buf + cnt, make_key(f32_to_key(sc), uint32_t(cb + c * 32 + j)));
               ++cnt;
             }
@@ -510,7 +575,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               need &= need - 1;
               const int n_r = __shfl_sync(full, int(cnt), r);
               const int64_t row_r = int64_t(m_tile) * BM + quarter * 32 + r;
-              uint64_t* buf_r = p.cand + (int64_t(split) * p.row_pad + row_r) * p.cap;
+              uint64_t* buf_r = p.cand + (int64_t(list_idx) * p.row_pad + row_r) * p.cap;
               const uint32_t vk = warp_compact_topk(buf_r, n_r, p.k, hist, list_stage, kListEntries, lane);
               if (lane == r) {
                 cnt = uint32_t(p.k);
@@ -581,12 +646,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));  // leader's barrier
           else mbar_arrive(tempty_bar(acc));
         }
-        if (++acc == ACC_STAGES) {
+        if (WIDE) {
+          acc_phase ^= 1u;  // this set's buffer is reused every second tile
+        } else if (++acc == ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
-      if (EPI == EPI_TOPK && tile_valid) p.counts[int64_t(split) * p.row_pad + row] = row_valid ? int32_t(cnt) : 0;
+      if (EPI == EPI_TOPK && tile_valid) p.counts[int64_t(list_idx) * p.row_pad + row] = row_valid ? int32_t(cnt) : 0;
       if (EPI == EPI_MAXTOK && c1 > c0) {
         float x = run_max;
         if (p.relu) x = fmaxf(x, 0.0f);
@@ -663,10 +730,10 @@ struct ProfileEvents {
 };
 ProfileEvents& profile_events();  // thread-local, defined in api.cu
 
-template <int EPI, int CL, bool PAIR = false, bool BIGLIST = false>
+template <int EPI, int CL, bool PAIR = false, bool BIGLIST = false, bool WIDE = false>
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
-  auto kern = umma_gemm_kernel<EPI, CL, PAIR, BIGLIST>;
+  auto kern = umma_gemm_kernel<EPI, CL, PAIR, BIGLIST, WIDE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
@@ -674,7 +741,7 @@ inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(grid));
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(WIDE ? GEMM_THREADS_WIDE : GEMM_THREADS);
   cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

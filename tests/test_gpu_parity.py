@@ -150,6 +150,25 @@ def test_flatip_mrl_prefix_and_scales():
         oracle.check_topk_parity(_np(s2), _np(i2), ref, 20, rtol=1e-3)
 
 
+def test_flatip_mrl_scales_large_batch_team_schedule():
+    """MRL prefix scoring on the large-batch path (cta_group::2 pairs, team schedule with a multi-tile window, folded
+    threshold filter with exact re-check): ids and scores against the fp32 oracle."""
+    gen = torch.Generator().manual_seed(11)
+    Q, N, d, m, k = 2100, 40000, 256, 128, 50
+    qf = torch.randn(Q, d, generator=gen).bfloat16()
+    cf = (torch.randn(N, d, generator=gen) * (0.5 + torch.rand(N, 1, generator=gen))).bfloat16()
+    qs = 1.0 / qf[:, :m].float().norm(dim=1)
+    cs = 1.0 / cf[:, :m].float().norm(dim=1)
+    s, i = lr.flatip_topk(qf.cuda(), cf.cuda(), k, d_used=m, q_scale=qs.cuda(), c_scale=cs.cuda())
+    ref = (F.normalize(qf[:, :m].float(), dim=-1) @ F.normalize(cf[:, :m].float(), dim=-1).T).numpy()
+    oracle.check_topk_parity(_np(s), _np(i), ref, k, rtol=1e-3)
+    # compact storage [N, m] without scales takes the same schedule
+    qn = F.normalize(qf[:, :m].float(), dim=-1).bfloat16()
+    cn = F.normalize(cf[:, :m].float(), dim=-1).bfloat16()
+    s2, i2 = lr.flatip_topk(qn.cuda(), cn.cuda(), k)
+    oracle.check_topk_parity(_np(s2), _np(i2), (qn.float() @ cn.float().T).numpy(), k, rtol=1e-3)
+
+
 def test_flatip_adversarial_order_stays_exact():
     """Scores ascending with the document id: every document beats the running threshold, so the candidate lists
     overflow and are compacted over and over — the result must still be exact."""
