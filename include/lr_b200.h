@@ -96,9 +96,12 @@ int lr_lasttoken_head(const void* hidden, int hidden_dtype, const int64_t* mask,
  *   (-inf, -1) (Faiss convention for missing results).
  *   out_keys   optional [Q,k] u64 sorted candidate keys (for the cross-GPU merge), may be NULL
  *   Ties: equal scores are ordered by ascending id (Faiss leaves this undefined).
- *   workspace: >= lr_flatip_workspace_bytes(Q, N, k) bytes, 256-byte aligned.
+ *   workspace: >= lr_flatip_workspace_bytes_for(Q, N, k, d_used) bytes, 256-byte aligned.
+ *              lr_flatip_workspace_bytes(Q, N, k) is the bound over every d_used (short rows, d_used <= 768,
+ *              keep two candidate lists per corpus split and need about twice the space of full-width rows).
  * ------------------------------------------------------------------------- */
 size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k);
+size_t lr_flatip_workspace_bytes_for(int64_t Q, int64_t N, int k, int64_t d_used);
 int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
                    int64_t Q, int64_t N, int64_t d_used,
                    const float* q_scale, const float* c_scale, int64_t id_offset, int k,

@@ -26,6 +26,7 @@ PROTOTYPES = {
     "lr_embbag_encode": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
     "lr_lasttoken_head": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
     "lr_flatip_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "lr_flatip_workspace_bytes_for": (_sz, [_i64, _i64, _i32, _i64]),
     "lr_flatip_topk": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lr_flatip_scores": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "lr_flatip_last_plan": (_i32, [_vp]),

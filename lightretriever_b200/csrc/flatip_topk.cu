@@ -304,9 +304,16 @@ __global__ void carry_topk_kernel(const uint64_t* __restrict__ merged, int64_t k
 
 using namespace lr;
 
+extern "C" size_t lr_flatip_workspace_bytes_for(int64_t Q, int64_t N, int k, int64_t d_used) {
+  if (Q < 1 || N < 1 || k < 1 || d_used < 1) return 0;
+  return make_plan(Q, N, k, d_used).total_bytes;
+}
+
 extern "C" size_t lr_flatip_workspace_bytes(int64_t Q, int64_t N, int k) {
   if (Q < 1 || N < 1 || k < 1) return 0;
-  return make_plan(Q, N, k, 4096).total_bytes >= make_plan(Q, N, k, 64).total_bytes ? make_plan(Q, N, k, 4096).total_bytes : make_plan(Q, N, k, 64).total_bytes;
+  // the plan depends on d_used only through its regime: short rows (two lists per split, refresh passes) or not
+  const size_t a = make_plan(Q, N, k, 4096).total_bytes, b = make_plan(Q, N, k, 64).total_bytes;
+  return a > b ? a : b;
 }
 
 // Plan of a (Q, N, k) search without running it (no device needed beyond the SM count): for tests and capacity planning.

@@ -57,7 +57,7 @@ def flatip_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, d_used: Optio
     if c.device != dev:
         raise ValueError("query and corpus must be on the same device")
     lib = _C.load()
-    ws = (workspace or _WS).get(lib.lr_flatip_workspace_bytes(Q, N, k), dev)
+    ws = (workspace or _WS).get(lib.lr_flatip_workspace_bytes_for(Q, N, k, d), dev)
     scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
     ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
     keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if return_keys else None

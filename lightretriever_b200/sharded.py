@@ -69,3 +69,42 @@ class ShardedFlatIPIndex:
         _, _, keys = flatip_topk(q, self.local.corpus, k, d_used=d_used, id_offset=self.lo, return_keys=True)
         gathered = exchange_candidates(keys, self.group)  # [world, Q, k]
         return topk_merge(gathered, k)
+
+
+class ShardedImpactIndex:
+    """Document-sharded sparse impact index: the sparse twin of ``ShardedFlatIPIndex`` ("same for CSR postings
+    — shard by doc, per-shard inverted index").  Rank r indexes documents ``[lo, hi)`` as its own token-major inverted index
+    (local doc ids, ``id_offset = lo``); a search runs ``lr_sparse_score_topk`` on the shard and only the per-shard top-k
+    keys ``[Q, k]`` u64 (integer score << 32 | ~global id) cross NVLink, then ``lr_topk_merge`` with integer scores.  The
+    reference has no multi-GPU sparse path (Anserini is one JVM, retriever/anserini_search.py:143-216); the exchange is the
+    one the dense path uses."""
+
+    def __init__(self, vocab_size: int, n_total: int, device: Optional[torch.device] = None, group=None):
+        from .sparse_search import ImpactIndex  # requires the CUDA library
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = int(n_total)
+        self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
+        if self.n_total >= (1 << 32) - 2:
+            raise ValueError("global ids must stay below 2^32")
+        self.local = ImpactIndex(vocab_size, device=device, id_offset=self.lo)
+
+    def add_local_csr(self, indptr, tok, imp) -> None:
+        """Append documents of this rank's shard (global ids lo .. hi-1, in order) as doc-major CSR."""
+        self.local.add_csr(indptr, tok, imp)
+        if self.local.N > self.hi - self.lo:
+            raise ValueError("more documents than this rank's shard holds")
+
+    def search_device(self, q_indptr, q_tok, q_cnt, k: int):
+        from . import _C
+        from .search import topk_merge
+
+        if self.local.N != self.hi - self.lo:
+            raise RuntimeError(f"shard incomplete: {self.local.N} of {self.hi - self.lo} documents")
+        if self.world == 1:
+            return self.local.search_device(q_indptr, q_tok, q_cnt, k)
+        _, _, keys = self.local.search_device(q_indptr, q_tok, q_cnt, k, return_keys=True)
+        gathered = exchange_candidates(keys, self.group)  # [world, Q, k]
+        return topk_merge(gathered, k, score_kind=_C.LR_SCORE_U32)

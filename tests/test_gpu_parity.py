@@ -431,6 +431,43 @@ def test_sparse_score_wide_scores_take_the_int32_pass():
         np.testing.assert_array_equal(_np(s), es)
 
 
+def test_sparse_score_document_shards_merge_to_the_global_topk():
+    """Multi-GPU sparse path on one device: per-shard inverted indexes with id offsets -> per-shard top-k keys
+    -> lr_topk_merge with integer scores == the unsharded search == the oracle.  (The exchange itself is covered by the
+    world-2 gloo test; ShardedImpactIndex with world == 1 must equal the plain index.)"""
+    from lightretriever_b200 import _C as C
+    from lightretriever_b200.sharded import shard_range
+    from lightretriever_b200.sparse_search import parse_queries
+    rng = np.random.default_rng(21)
+    N, V, k, world = 9001, 300, 64, 3
+    docs = _rand_docs(rng, N, V, 12)
+    ip = np.zeros(N + 1, np.int64)
+    tok, imp = [], []
+    for j, d in enumerate(docs):
+        tok += [int(t) for t in d]
+        imp += list(d.values())
+        ip[j + 1] = len(tok)
+    tok, imp = np.asarray(tok, np.int32), np.asarray(imp, np.int32)
+    queries = [" ".join(str(int(t)) for t in rng.integers(0, V, size=int(rng.integers(1, 20)))) for _ in range(33)]
+    qi, qt, qc = parse_queries(queries, V)
+    keys = []
+    for r in range(world):
+        lo, hi = shard_range(N, r, world)
+        shard = lr.ImpactIndex(V, id_offset=lo)
+        shard.add_csr(ip[lo:hi + 1] - ip[lo], tok[ip[lo]:ip[hi]], imp[ip[lo]:ip[hi]])
+        keys.append(shard.search_device(qi, qt, qc, k, return_keys=True)[2])
+    s, i = lr.topk_merge(torch.stack(keys, 0).contiguous(), k, score_kind=C.LR_SCORE_U32)
+    es, ei = oracle.impact_topk([oracle.query_counts([int(t) for t in q.split()]) for q in queries],
+                                [{int(a): b for a, b in d.items()} for d in docs], k)
+    np.testing.assert_array_equal(_np(i), ei)
+    np.testing.assert_array_equal(_np(s), es)
+    whole = lr.ShardedImpactIndex(V, N)  # world == 1 here
+    whole.add_local_csr(ip, tok, imp)
+    s1, i1 = whole.search_device(qi, qt, qc, k)
+    np.testing.assert_array_equal(_np(i1), ei)
+    np.testing.assert_array_equal(_np(s1), es)
+
+
 def test_sparse_head_to_sparse_search_roundtrip():
     """K3 output (CSR) feeds K4 directly, and through the reference's JSON form, with identical results."""
     gen = torch.Generator().manual_seed(9)

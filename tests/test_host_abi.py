@@ -66,7 +66,8 @@ def test_flatip_plan_invariants():
         assert p["prefix_units"] == (groups * p["prefix_splits"] if p["prefix_tiles"] else 0)
         assert p["grid"] % p["cl"] == 0 and 1 <= p["grid"] <= 148
         assert p["pair"] in (0, 1) and (not p["pair"] or p["cl"] == 2)
-        assert p["ws"] == lib.lr_flatip_workspace_bytes(Q, N, k) > 0
+        assert 0 < p["ws"] == lib.lr_flatip_workspace_bytes_for(Q, N, k, 4096) <= lib.lr_flatip_workspace_bytes(Q, N, k)
+        assert lib.lr_flatip_workspace_bytes_for(Q, N, k, 128) <= lib.lr_flatip_workspace_bytes(Q, N, k)
     head = _plan(10000, 8_800_000, 100)
     assert (head["cl"], head["pair"], head["prefix_tiles"], head["cap"]) == (2, 1, 128, 256)   # cta_group::2 pair on the team schedule, 32768-doc prefix
     big_k = _plan(10000, 8_800_000, 1000)

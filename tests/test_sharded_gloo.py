@@ -38,6 +38,25 @@ def _worker(rank, world, port, out_dir):
         fs, fi = oracle.flatip_topk(q, corpus, k)
         np.testing.assert_array_equal(mi, fi)
         np.testing.assert_array_equal(ms, fs)
+        # sparse twin: document-sharded impact search, integer scores, same exchange
+        V, nd = 60, 403
+        docs = [{int(t): int(rng.integers(1, 300)) for t in rng.choice(V, size=int(rng.integers(0, 9)), replace=False)}
+                for _ in range(nd)]
+        queries = [{int(t): int(rng.integers(1, 3)) for t in rng.choice(V, size=6, replace=False)} for _ in range(4)]
+        lo, hi = shard_range(nd, rank, world)
+        ss, si = oracle.impact_topk(queries, docs[lo:hi], 15, id_offset=lo)
+        skeys = np.where(si >= 0, (ss.astype(np.uint64) << np.uint64(32)) |
+                         (np.uint64(0xFFFFFFFF) - np.where(si >= 0, si, 0).astype(np.uint64)), np.uint64(0))
+        g2 = exchange_candidates(torch.from_numpy(skeys.view(np.int64))).numpy().view(np.uint64)
+        assert g2.shape == (world, 4, 15)
+        sc = [np.where(g2[r] != 0, (g2[r] >> np.uint64(32)).astype(np.float32), -np.inf).astype(np.float32)
+              for r in range(world)]
+        ids = [np.where(g2[r] != 0, (np.uint64(0xFFFFFFFF) - (g2[r] & np.uint64(0xFFFFFFFF))).astype(np.int64), -1)
+               for r in range(world)]
+        ms2, mi2 = oracle.merge_topk(sc, ids, 15)
+        fs2, fi2 = oracle.impact_topk(queries, docs, 15)
+        np.testing.assert_array_equal(mi2, fi2)
+        np.testing.assert_array_equal(ms2, fs2)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
