@@ -115,10 +115,21 @@ embbag_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offse
     const TT* col = table + int64_t(c) * VN;
     int64_t i = 0;
     if (cached) {
+      // eight, then four independent 16-byte loads in flight (skipped ids read row 0 and are discarded); token order is
+      // preserved: the adds are issued in index order
+      for (; i + 8 <= len; i += 8) {
+        int64_t t[8];
+        uint4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = s_ids[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = ld_nc_v4(col + (t[u] >= 0 ? t[u] : 0) * d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t[u] >= 0) Vec16<TT>::add(r[u], acc);
+      }
       for (; i + 4 <= len; i += 4) {
         const int64_t a = s_ids[i], b = s_ids[i + 1], e = s_ids[i + 2], f = s_ids[i + 3];
-        // four independent 16-byte loads in flight (skipped ids read row 0 and are discarded);
-        // token order is preserved: the adds are issued in index order
         const uint4 ra = ld_nc_v4(col + (a >= 0 ? a : 0) * d);
         const uint4 rb = ld_nc_v4(col + (b >= 0 ? b : 0) * d);
         const uint4 re = ld_nc_v4(col + (e >= 0 ? e : 0) * d);
@@ -165,6 +176,77 @@ embbag_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offse
     }
   }
   if (bad && tid == 0 && err_flag) atomicOr(err_flag, 1);
+}
+
+// Narrow outputs (MRL prefixes of <= 32 16-byte chunks: 256 bf16 / 128 f32 columns): one WARP per bag, four bags per
+// CTA, no shared memory and no block barrier — a CTA per bag would leave 3/4 of its threads idle and spend its life in
+// the id-staging and reduction barriers.  Lane c owns chunk c; the ids of 32 tokens are staged one per lane and
+// broadcast by shuffle; eight row loads per lane are in flight; adds stay in token order.
+template <typename TT, typename TO>
+__global__ void __launch_bounds__(EB_THREADS)
+embbag_warp_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ offsets, int64_t n_ids, int64_t n_bags,
+                   const TT* __restrict__ table, int64_t V, int64_t d, int64_t padding_idx, int out_dim, int normalize,
+                   TO* __restrict__ out, int32_t* err_flag) {
+  constexpr int VN = Vec16<TT>::N;
+  const uint32_t full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int64_t bag = int64_t(blockIdx.x) * (EB_THREADS / 32) + (threadIdx.x >> 5);
+  if (bag >= n_bags) return;
+  const int64_t beg = offsets[bag];
+  const int64_t end = (bag + 1 < n_bags) ? offsets[bag + 1] : n_ids;
+  const int64_t len = end > beg ? end - beg : 0;
+  const int nchunks = out_dim / VN;  // <= 32
+  const bool active = lane < nchunks;
+  const TT* col = table + int64_t(active ? lane : 0) * VN;
+  float acc[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+  int cnt = 0;
+  bool bad = false;
+  for (int64_t base = 0; base < len; base += 32) {
+    int64_t id = -1;  // -1: skipped (padding, invalid, past the end)
+    if (base + lane < len) {
+      id = ids[beg + base + lane];
+      if (id == padding_idx) {
+        id = -1;
+      } else if (id < 0 || id >= V) {
+        bad = true;
+        id = -2;  // counted like torch counts it, never read
+      }
+    }
+    cnt += __popc(__ballot_sync(full, id != -1));
+    const int nb = int(len - base < 32 ? len - base : 32);
+    for (int u0 = 0; u0 < nb; u0 += 8) {
+      int64_t t[8];
+      uint4 r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __shfl_sync(full, id, (u0 + u) & 31);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r[u] = ld_nc_v4(col + (t[u] >= 0 ? t[u] : 0) * d);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u0 + u < nb && t[u] >= 0) Vec16<TT>::add(r[u], acc);
+    }
+  }
+  bad = __any_sync(full, bad);
+  float sumsq = 0.f;
+#pragma unroll
+  for (int j = 0; j < VN; ++j) {
+    acc[j] = (cnt > 0 && active) ? acc[j] / float(cnt) : 0.0f;  // torch divides the fp32 sum by the count
+    sumsq += acc[j] * acc[j];
+  }
+  float scale = 1.0f;
+  if (normalize) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sumsq += __shfl_xor_sync(full, sumsq, off);
+    scale = 1.0f / fmaxf(sqrtf(sumsq), 1e-12f);  // F.normalize divides by max(norm, eps)
+  }
+  if (active) {
+    TO* o = out + bag * int64_t(out_dim) + lane * VN;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) store_out<TO>(o + j, bad ? __int_as_float(0x7FC00000) : acc[j] * scale);
+  }
+  if (bad && lane == 0 && err_flag) atomicOr(err_flag, 1);
 }
 
 // ---- K1b: last-token index (dense_pooling.py:48-55)
@@ -254,11 +336,24 @@ extern "C" int lr_embbag_encode(const int64_t* ids, const int64_t* offsets, int6
   embbag_kernel<TT, TO><<<grid, EB_THREADS, smem, st>>>(ids, offsets, n_ids, n_bags, static_cast<const TT*>(table), V, \
                                                         d, padding_idx, int(out_dim), normalize,                \
                                                         static_cast<TO*>(out), err_flag)
-  if (table_dtype == LR_BF16 && out_dtype == LR_BF16) LR_EB_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  const int vn = table_dtype == LR_BF16 ? 8 : 4;
+  const bool narrow = out_dim / vn <= 32;  // one warp per bag
+  const dim3 wgrid{unsigned((n_bags + EB_THREADS / 32 - 1) / (EB_THREADS / 32))};
+#define LR_EBW_LAUNCH(TT, TO)                                                                                     \
+  embbag_warp_kernel<TT, TO><<<wgrid, EB_THREADS, 0, st>>>(ids, offsets, n_ids, n_bags, static_cast<const TT*>(table), \
+                                                           V, d, padding_idx, int(out_dim), normalize,          \
+                                                           static_cast<TO*>(out), err_flag)
+  if (narrow) {
+    if (table_dtype == LR_BF16 && out_dtype == LR_BF16) LR_EBW_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+    else if (table_dtype == LR_BF16) LR_EBW_LAUNCH(__nv_bfloat16, float);
+    else if (out_dtype == LR_BF16) LR_EBW_LAUNCH(float, __nv_bfloat16);
+    else LR_EBW_LAUNCH(float, float);
+  } else if (table_dtype == LR_BF16 && out_dtype == LR_BF16) LR_EB_LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (table_dtype == LR_BF16) LR_EB_LAUNCH(__nv_bfloat16, float);
   else if (out_dtype == LR_BF16) LR_EB_LAUNCH(float, __nv_bfloat16);
   else LR_EB_LAUNCH(float, float);
 #undef LR_EB_LAUNCH
+#undef LR_EBW_LAUNCH
   LR_LAUNCH_CHECK();
   return LR_OK;
 }

@@ -616,3 +616,42 @@ def test_full_width_properties_at_scale():
     torch.testing.assert_close(s, rec, rtol=1e-2, atol=1e-4)
     ref = q[:32].float() @ c.float().T
     oracle.check_topk_parity(_np(s[:32]), _np(i[:32]), ref.cpu().numpy(), k, rtol=1e-2)
+
+
+def test_short_rows_at_scale_refresh_passes_and_two_epilogue_sets():
+    """BASELINE configs[2] regime at a size where every large-batch mechanism is on (plan checked below): 32768-document
+    prefix, threshold-refresh passes, cta_group::2 pairs on the team schedule, two epilogue warp sets with their own
+    candidate lists.  Properties (planted documents, order, unique ids, fp32 recomputation of the returned scores) for
+    every query; full parity against an fp32 matmul of the same bf16 values for a sample of queries."""
+    torch.manual_seed(13)
+    Q, N, d, m, k = 2304, 1_200_000, 256, 128, 100
+    c = torch.randn(N, d, device="cuda").bfloat16()
+    q = torch.randn(Q, d, device="cuda").bfloat16()
+    planted = torch.randperm(N, device="cuda")[:Q]
+    c[planted, :m] = q[:, :m]
+    cs = (1.0 / c[:, :m].float().norm(dim=1)).contiguous()
+    qs = (1.0 / q[:, :m].float().norm(dim=1)).contiguous()
+    for scaled in (True, False):
+        if scaled:  # full-width rows scored on the first m columns with reciprocal prefix norms
+            s, i = lr.flatip_topk(q, c, k, d_used=m, q_scale=qs, c_scale=cs)
+            qn, cn = q[:, :m].float() * qs[:, None], None
+        else:       # compact storage [N, m], already normalised
+            qq = F.normalize(q[:, :m].float(), dim=-1).bfloat16()
+            cc = F.normalize(c[:, :m].float(), dim=-1).bfloat16()
+            s, i = lr.flatip_topk(qq, cc, k)
+            qn = qq.float()
+        assert bool((i[:, 0] == planted).all())
+        assert bool((s[:, :-1] >= s[:, 1:]).all())
+        assert all(len(set(row)) == k for row in i[:16].tolist())
+        rows = (c[i][:, :, :m].float() * cs[i][:, :, None]) if scaled else cc[i].float()
+        rec = torch.einsum("qd,qkd->qk", qn, rows)
+        torch.testing.assert_close(s, rec, rtol=1e-3, atol=1e-5)
+        full = (c[:, :m].float() * cs[:, None]) if scaled else cc.float()
+        ref = qn[:24] @ full.T
+        oracle.check_topk_parity(_np(s[:24]), _np(i[:24]), ref.cpu().numpy(), k, rtol=1e-3)
+        del full, ref, rows, rec
+    from lightretriever_b200 import _C as C
+    import ctypes
+    out = (ctypes.c_int64 * 16)()
+    C.load().lr_flatip_plan(Q, N, k, out)
+    assert out[1] == 1 and out[5] == 128  # pairs + the 32768-document prefix: the regime this test is about
