@@ -15,9 +15,10 @@
 
 namespace lr {
 
-int topk_merge_strided(const uint64_t* keys, const int32_t* counts, int L, int64_t Q, int64_t q_stride, int cap, int k,
-                       int score_kind, int64_t id_offset, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
-                       int64_t out_key_stride, cudaStream_t st);
+int topk_merge_two_level(const uint64_t* keys, const int32_t* counts, int L, int64_t Q, int64_t q_stride, int cap, int k,
+                         int score_kind, int64_t id_offset, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                         int64_t out_key_stride, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t topk_merge_scratch_bytes(int L, int64_t Q, int cap, int k);
 
 struct PassPlan {
   int tile_begin, tile_end, splits, units, grid, rounds;
@@ -36,7 +37,7 @@ struct FlatipPlan {
   int wide;  // two epilogue warp sets (umma_gemm.cuh WIDE): every split owns TWO candidate lists
   int lmul;  // candidate lists per split (1 or 2)
   int max_lists;  // lists of the widest pass + 1 (the carried top-k)
-  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, off_carry, off_teamctr, total_bytes;
+  size_t off_gthr, off_counts, off_cand, off_pcounts, off_pcand, off_carry, off_teamctr, off_merge, merge_bytes, total_bytes;
 };
 
 // Team schedule of the main pass: bands of g row groups; inside a band the clusters form floor(nc / g) fixed teams, each
@@ -163,7 +164,7 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
     // Small query batches (online serving, HBM-bound): a prefix of one tile per cluster, every cluster scoring a
     // different tile, costs one tile time and removes the cold-start cuts, which otherwise pile up in the one or two
     // epilogue warps that own the few valid query rows.
-    if (want < 0 && pl.m_groups < 4 && Q >= 4) {  // a single query cuts its list in ~20k cycles: not worth a pass
+    if (want < 0 && pl.m_groups < 4 && Q >= 4) {  // one query: measured 1.37 ms single-phase vs 1.47 ms with the pass
       const int s0 = geo.n_clusters / pl.m_groups;
       if (s0 >= 8 && pl.n_tiles >= 8 * s0 && 4 * int64_t(k) <= int64_t(s0) * BN) {
         prefix_tiles = s0;
@@ -216,7 +217,12 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
   pl.off_pcand = align(pl.off_pcounts + size_t(pl.prefix.splits) * pl.lmul * pl.q_pad * 4);
   pl.off_carry = align(pl.off_pcand + size_t(pl.prefix.splits) * pl.lmul * pl.q_pad * pl.cap * 8);
   pl.off_teamctr = align(pl.off_carry + (prefix_tiles > 0 ? size_t(pl.q_pad) * pl.cap * 8 : 0));
-  pl.total_bytes = align(pl.off_teamctr + size_t(pl.main.n_bands) * size_t(pl.n_clusters) * 4 + 256);
+  pl.off_merge = align(pl.off_teamctr + size_t(pl.main.n_bands) * size_t(pl.n_clusters) * 4 + 256);
+  // scratch of the two-level merges (few queries, many lists: the online shapes)
+  pl.merge_bytes = topk_merge_scratch_bytes(main_lists, Q, pl.cap, k);
+  const size_t pm = topk_merge_scratch_bytes(pl.prefix.splits * pl.lmul, Q, pl.cap, k);
+  if (pm > pl.merge_bytes) pl.merge_bytes = pm;
+  pl.total_bytes = align(pl.off_merge + pl.merge_bytes);
   return pl;
 }
 
@@ -393,10 +399,10 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
     if (r) return r;
     const int lists = own_lists + (two_phase ? 1 : 0);
     if (last)
-      return topk_merge_strided(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, id_offset, out_scores, out_ids,
-                                out_keys, k, st);
-    return topk_merge_strided(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0, nullptr, nullptr, carry,
-                              pl.cap, st);
+      return topk_merge_two_level(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, id_offset, out_scores, out_ids,
+                                  out_keys, k, ws + pl.off_merge, pl.merge_bytes, st);
+    return topk_merge_two_level(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0, nullptr, nullptr, carry,
+                                pl.cap, ws + pl.off_merge, pl.merge_bytes, st);
   };
   if (two_phase) {
     // ---- phase A: prefix -> merged top-k in `carry`
@@ -407,8 +413,8 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
     LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
     rc = launch_pass<EPI_TOPK>(pl, pl.prefix, tmA, tmB, prm, st);
     if (!rc)
-      rc = topk_merge_strided(prm.cand, prm.counts, pl.prefix.splits * pl.lmul, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0,
-                              nullptr, nullptr, carry, pl.cap, st);
+      rc = topk_merge_two_level(prm.cand, prm.counts, pl.prefix.splits * pl.lmul, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0,
+                                nullptr, nullptr, carry, pl.cap, ws + pl.off_merge, pl.merge_bytes, st);
     profile_events() = pe_saved;
     if (rc) return rc;
   } else if (!(debug & 2)) {  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)

@@ -25,6 +25,11 @@
 
 namespace lr {
 
+int topk_merge_two_level(const uint64_t* keys, const int32_t* counts, int L, int64_t Q, int64_t q_stride, int cap, int k,
+                         int score_kind, int64_t id_offset, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                         int64_t out_key_stride, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t topk_merge_scratch_bytes(int L, int64_t Q, int cap, int k);
+
 constexpr int SS_TOUCH_CAP = 512;  // touched-accumulator list per warp; a step that touches more scans the block
 constexpr int SS_BATCH = 4;        // postings per lane whose loads are in flight together
 constexpr int SS_MAX_WARPS = 20;
@@ -363,7 +368,7 @@ struct SSPlan {
   int bd, nblk, S, cap;
   int warps[2], warp_bytes[2];  // [0] = 16-bit accumulators, [1] = int32 accumulators
   int grid[2];
-  size_t smem[2], off_counts, off_floor, off_cand, total_bytes;
+  size_t smem[2], off_counts, off_floor, off_cand, off_merge, merge_bytes, total_bytes;
 };
 
 static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
@@ -396,7 +401,9 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   pl.off_counts = 0;
   pl.off_floor = align(size_t(pl.S) * Q * 4);
   pl.off_cand = align(pl.off_floor + 2 * size_t(Q) * 4 + 256);  // 2 x floor_q [Q], 2 unit counters, the overflow flag
-  pl.total_bytes = align(pl.off_cand + size_t(pl.S) * Q * pl.cap * 8);
+  pl.off_merge = align(pl.off_cand + size_t(pl.S) * Q * pl.cap * 8);
+  pl.merge_bytes = topk_merge_scratch_bytes(pl.S, Q, pl.cap, k);
+  pl.total_bytes = align(pl.off_merge + pl.merge_bytes);
   return pl;
 }
 
@@ -493,6 +500,6 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   p.warp_bytes = pl.warp_bytes[1];
   rc = ss_dispatch<int32_t>(p, pl, st);  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
   if (rc != LR_OK) return rc;
-  return lr_topk_merge(p.cand, p.counts, pl.S, Q, Q, pl.cap, k, LR_SCORE_U32, id_offset, out_scores, out_ids, out_keys,
-                       stream);
+  return topk_merge_two_level(p.cand, p.counts, pl.S, Q, Q, pl.cap, k, LR_SCORE_U32, id_offset, out_scores, out_ids,
+                              out_keys, k, ws + pl.off_merge, pl.merge_bytes, st);
 }

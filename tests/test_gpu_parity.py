@@ -655,3 +655,27 @@ def test_short_rows_at_scale_refresh_passes_and_two_epilogue_sets():
     out = (ctypes.c_int64 * 16)()
     C.load().lr_flatip_plan(Q, N, k, out)
     assert out[1] == 1 and out[5] == 128  # pairs + the 32768-document prefix: the regime this test is about
+
+
+def test_online_searcher_graph_replay_matches_eager():
+    """The captured online step (encode -> flat-IP top-k -> merge) must return what the eager calls return, for requests
+    of different sizes replayed through the same graph (padding ids, empty unused bags)."""
+    gen = torch.Generator().manual_seed(5)
+    V, d, N, k = 3000, 256, 50_000, 20
+    table = (torch.randn(V, d, generator=gen) * 0.02).bfloat16().cuda()
+    corpus = F.normalize(torch.randn(N, d, generator=gen), dim=-1).bfloat16().cuda()
+    bag = lr.B200EmbeddingBag.from_pretrained(table, padding_idx=V - 1)
+    srv = lr.OnlineSearcher(bag, corpus, k, batch=8, max_tokens=8 * 32, id_offset=77)
+    for n_bags in (1, 5, 8):
+        lens = torch.randint(1, 33, (n_bags,), generator=gen)
+        ids = torch.randint(0, V - 1, (int(lens.sum()),), generator=gen).cuda()
+        offs = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.long), lens[:-1]]), 0).cuda()
+        s, i = srv.search(ids, offs)
+        qv = bag.encode(ids, offs, normalize=True)
+        es, ei = lr.flatip_topk(qv, corpus, k, id_offset=77)
+        np.testing.assert_array_equal(_np(i), _np(ei))
+        np.testing.assert_array_equal(_np(s), _np(es))
+        ref = (qv.float().cpu() @ corpus.float().cpu().T).numpy()
+        oracle.check_topk_parity(_np(s), _np(i), ref, k, rtol=1e-2, id_offset=77)
+    with pytest.raises(ValueError):
+        srv.search(torch.zeros(9 * 32, dtype=torch.long).cuda(), torch.zeros(9, dtype=torch.long).cuda())
