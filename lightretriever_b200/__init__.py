@@ -4,7 +4,8 @@ Hand-written sm_100a CUDA kernels (csrc/) behind a C ABI (include/lr_b200.h, lib
 host layer that keeps the reference's encode / index / retrieve_with_emb / search interfaces.  No CPU fallback.
 """
 from . import _C  # noqa: F401  (ctypes binding; `_C.load()` builds/loads liblr_b200.so)
-from .encode import B200EmbeddingBag, flatten_token_ids, lasttoken_head, tokenize_nonctx_qry_emb_bag
+from .encode import (B200EmbeddingBag, construct_embedding_bag, emb_bag_inputs, flatten_token_ids, lasttoken_head,
+                     tokenize_nonctx_qry_emb_bag)
 from .search import FlatIPIndex, FlatIPSearch, encode_keys, flatip_scores, flatip_topk, topk_merge
 from .sharded import ShardedFlatIPIndex, ShardedImpactIndex, exchange_candidates, shard_range
 from .sparse_head import (aggregate, convert_sparse_reps_to_json, csr_to_json, get_sparse_attention_mask,

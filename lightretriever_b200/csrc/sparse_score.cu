@@ -18,7 +18,7 @@
 //      than SS_TOUCH_CAP slots scans the block); entries beating the unit's running 64-bit threshold key — and the
 //      query's global score floor, raised with atomicMax by every unit of that query — are appended to the warp's
 //      candidate list; a full list is cut to its exact top-k by a warp-level 64-bit radix select.
-// The unit's list goes to the workspace and lr_topk_merge produces the sorted result.  Integer-exact.
+// The unit's list goes to the workspace and the (two-level, for few queries) merge of topk_merge.cu produces the sorted result.  Integer-exact.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -106,6 +106,44 @@ class B200EmbeddingBag:
     __call__ = forward
 
 
+def emb_bag_inputs(prompt_token_ids: Sequence[int], eos_token_id: int, start: int, end: int,
+                   device=None) -> torch.Tensor:
+    """Input ids of one table-construction batch: ``[bos] + prompt + [vocab id] + [eos]`` for vocab ids ``start..end-1``
+    (reference finetune/nonctx_emb_utils.py:270-296; ``prompt_token_ids`` already holds the bos when the tokenizer adds one)."""
+    n, p = end - start, len(prompt_token_ids)
+    ids = torch.zeros((n, p + 2), dtype=torch.long, device=device)
+    if p:
+        ids[:, :p] = torch.tensor([list(prompt_token_ids)], dtype=torch.long, device=device)
+    ids[:, -2] = torch.arange(start, end, dtype=torch.long, device=device)
+    ids[:, -1] = eos_token_id
+    return ids
+
+
+def construct_embedding_bag(model, tokenizer, prompt: Optional[str] = None, batch_size: int = 2000,
+                            table_dtype: torch.dtype = torch.float32) -> B200EmbeddingBag:
+    """Builds the query encoder's table exactly as the reference does (finetune/nonctx_emb_utils.py:239-313): row v is the
+    backbone's last-position hidden state of ``[bos] + prompt + [v] + [eos]`` for every v in ``[0, len(tokenizer))``,
+    accumulated in fp32; ``padding_idx = tokenizer.pad_token_id``.  The LLM backbone is the caller's untouched torch module
+    (north star: "PyTorch ... for the untouched LLM backbone"); what changes is the object returned — a ``B200EmbeddingBag``
+    (``table_dtype=torch.bfloat16`` gives the table the reference's notebook serves, scripts/asymmetric_dense_infer.ipynb:50)."""
+    model.eval()
+    bos, eos, pad = tokenizer.bos_token_id, tokenizer.eos_token_id, tokenizer.pad_token_id
+    n_vocab = len(tokenizer)
+    add_bos = bos in tokenizer.encode("", add_special_tokens=True)  # fast tokenizers add it without exposing a switch
+    prompt_ids = list(tokenizer.encode(prompt, add_special_tokens=False)) if prompt is not None else []
+    if add_bos:
+        prompt_ids.insert(0, bos)
+    dev = model.device
+    table = torch.zeros((n_vocab, model.config.hidden_size), dtype=torch.float32, device=dev)
+    for start in range(0, n_vocab, batch_size):
+        end = min(start + batch_size, n_vocab)
+        ids = emb_bag_inputs(prompt_ids, eos, start, end, device=dev)
+        with torch.no_grad(), torch.autocast(device_type=dev.type):
+            out = model(input_ids=ids, return_dict=True, use_cache=False, output_hidden_states=False)
+        table[start:end] = out.last_hidden_state[:, -1]
+    return B200EmbeddingBag.from_pretrained(table.to(table_dtype), padding_idx=pad)
+
+
 def tokenize_nonctx_qry_emb_bag(queries: Sequence[str], tokenizer, max_len: int = 512) -> dict:
     """Host restatement of reference finetune/nonctx_emb_utils.py:197-219 (flattened ids + bag offsets)."""
     encodings_ids = tokenizer(list(queries), max_length=max_len, truncation=True, add_special_tokens=False,

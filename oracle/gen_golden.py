@@ -28,6 +28,7 @@ def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference tree not mounted; golden vectors can only be generated in the build container")
     sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))  # tests/: the fake backbone shared with the tests
     os.makedirs(OUT, exist_ok=True)
     meta = {"generator": "oracle/gen_golden.py", "torch": torch.__version__, "imported": []}
     g = torch.Generator().manual_seed(1234)
@@ -140,6 +141,19 @@ def main():
         meta["imported"].append("lightretriever.finetune.nonctx_emb_utils.tokenize_nonctx_qry_emb_bag")
     except Exception as e:  # recorded, not fatal: the oracle restates those two lines
         meta["flatten_import_error"] = repr(e)[:300]
+
+    # ---------------------------------------------------------------- table construction (construct_embedding_bag)
+    try:
+        from lightretriever.finetune.nonctx_emb_utils import construct_embedding_bag
+        from tests_support_fake_backbone import FakeBackbone, FakeTokenizer  # tests/tests_support_fake_backbone.py
+        for name, add_bos, prompt in (("embbag_table_bos_prompt", True, "query: "), ("embbag_table_plain", False, None)):
+            tok, mdl = FakeTokenizer(n_vocab=53, add_bos=add_bos), FakeBackbone(n_vocab=53, hidden=8)
+            ref_bag = construct_embedding_bag(mdl, tok, prompt=prompt, batch_size=20)
+            np.savez(os.path.join(OUT, name + ".npz"), table=ref_bag.weight.detach().numpy(),
+                     padding_idx=ref_bag.padding_idx, inputs_seen=np.concatenate(mdl.seen, 0))
+        meta["imported"].append("lightretriever.finetune.nonctx_emb_utils.construct_embedding_bag")
+    except Exception as e:
+        meta["construct_import_error"] = repr(e)[:300]
 
     with open(os.path.join(OUT, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)

@@ -43,6 +43,14 @@ def flatten_token_ids(token_id_lists: Sequence[Sequence[int]]):
     return input_ids, offsets
 
 
+def emb_bag_table_inputs(prompt_token_ids: Sequence[int], eos_token_id: int, start: int, end: int) -> np.ndarray:
+    """finetune/nonctx_emb_utils.py:270-296: rows ``prompt (with bos) + [v] + [eos]`` for v in [start, end) — plain loops."""
+    rows = []
+    for v in range(start, end):
+        rows.append(list(prompt_token_ids) + [v, eos_token_id])
+    return np.asarray(rows, dtype=np.int64).reshape(end - start, len(prompt_token_ids) + 2)
+
+
 def embbag_encode(ids, offsets, table, padding_idx: Optional[int] = None, shrink_dim: Optional[int] = None,
                   normalize: bool = False) -> torch.Tensor:
     """finetune/modeling_hybrid.py:474 (emb_bag.forward) + :487-488 (shrink) + :489-490 (F.normalize), fp32.

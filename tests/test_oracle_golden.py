@@ -119,3 +119,27 @@ def test_impact_formula_matches_notebook_definition():
     s, i = oracle.impact_topk(qs, docs, 3)
     assert i.tolist() == [[0, 1, 3], [-1, -1, -1], [3, 0, -1]]
     assert oracle.query_counts([4, 4, 9], "sum") == {4: 2, 9: 1} and oracle.query_counts([4, 4, 9], "bow") == {4: 1, 9: 1}
+
+
+def test_embedding_bag_table_construction_matches_reference(golden_dir):
+    """Row f4: ``construct_embedding_bag`` (finetune/nonctx_emb_utils.py:239-313) — the golden tables were produced by the
+    reference's own function driving the fake backbone of tests_support_fake_backbone.py; ours must feed the backbone the
+    same input ids in the same batches and return the same table and padding_idx (host logic: runs without a GPU)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from tests_support_fake_backbone import FakeBackbone, FakeTokenizer
+    import lightretriever_b200 as lr
+    for name, add_bos, prompt in (("embbag_table_bos_prompt", True, "query: "), ("embbag_table_plain", False, None)):
+        g = _load(golden_dir, name + ".npz")
+        tok, mdl = FakeTokenizer(n_vocab=53, add_bos=add_bos), FakeBackbone(n_vocab=53, hidden=8)
+        bag = lr.construct_embedding_bag(mdl, tok, prompt=prompt, batch_size=20)
+        np.testing.assert_array_equal(np.concatenate(mdl.seen, 0), g["inputs_seen"])
+        np.testing.assert_array_equal(bag.weight.numpy(), g["table"])
+        assert bag.padding_idx == int(g["padding_idx"]) and bag.weight.dtype == torch.float32
+        # the oracle's plain-loop restatement of the input layout
+        prompt_ids = ([tok.bos_token_id] if add_bos else []) + (tok.encode(prompt, add_special_tokens=False) if prompt else [])
+        np.testing.assert_array_equal(oracle.emb_bag_table_inputs(prompt_ids, tok.eos_token_id, 0, 53), g["inputs_seen"])
+        np.testing.assert_array_equal(lr.emb_bag_inputs(prompt_ids, tok.eos_token_id, 20, 40).numpy(), g["inputs_seen"][20:40])
+        b16 = lr.construct_embedding_bag(FakeBackbone(n_vocab=53, hidden=8), tok, prompt=prompt, batch_size=53,
+                                         table_dtype=torch.bfloat16)
+        np.testing.assert_array_equal(b16.weight.float().numpy(), torch.from_numpy(g["table"]).bfloat16().float().numpy())
