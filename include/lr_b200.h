@@ -125,6 +125,12 @@ int lr_set_profile_events(void* ev_begin, void* ev_end);
  * out[9]=main splits out[10]=main units out[11]=main grid (CTAs) out[12]=band (query tiles) out[13]=workspace bytes
  * out[14]=main rounds out[15]=concurrent clusters */
 int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16);
+/* The sequence of scoring passes of a (Q, N, k, d_used) search: warm-start prefix, threshold-refresh passes (short rows
+ * only), main pass.  Writes up to max_passes rows of 4 values {first tile, end tile, splits, team schedule (0|1)} and
+ * returns the number of passes (negative on error).  out_flags[0] = two epilogue warp sets (0|1),
+ * out_flags[1] = candidate lists per split. */
+int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used, int64_t* out_rows, int max_passes,
+                          int64_t* out_flags2);
 
 /* Plan of the last lr_flatip_topk call on this thread (for bench / DESIGN):
  * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=rounds */

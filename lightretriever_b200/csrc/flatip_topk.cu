@@ -337,6 +337,26 @@ extern "C" int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16) {
   return LR_OK;
 }
 
+extern "C" int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used, int64_t* out_rows, int max_passes,
+                                     int64_t* out_flags2) {
+  LR_CHECK_ARG(out_rows && out_flags2 && max_passes >= 1 && Q >= 1 && N >= 1 && k >= 1 && k <= 2048 && d_used >= 1,
+               "flatip_plan_passes: bad arguments");
+  const FlatipPlan pl = make_plan(Q, N, k, d_used);
+  int n = 0;
+  auto put = [&](const PassPlan& pp) {
+    if (n < max_passes) {
+      out_rows[4 * n + 0] = pp.tile_begin; out_rows[4 * n + 1] = pp.tile_end;
+      out_rows[4 * n + 2] = pp.splits; out_rows[4 * n + 3] = pp.sched;
+    }
+    ++n;
+  };
+  if (pl.prefix.units > 0) put(pl.prefix);
+  for (int i = 0; i < pl.n_mid; ++i) put(pl.mid[i]);
+  put(pl.main);
+  out_flags2[0] = pl.wide; out_flags2[1] = pl.lmul;
+  return n;
+}
+
 extern "C" int lr_flatip_last_plan(int64_t* out8) {
   const FlatipPlan& pl = g_last_plan;
   out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.main.splits; out8[3] = pl.main.band_size * pl.cl;

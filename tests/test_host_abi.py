@@ -159,3 +159,37 @@ def test_shard_ranges_partition_the_corpus():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         lr.shard_range(10, 3, 3)
+
+
+def test_flatip_passes_partition_the_corpus():
+    """Warm-start prefix, threshold-refresh passes and main pass must cover every corpus tile exactly once, in order, for
+    full-width and short rows alike; short rows with large batches refresh the thresholds and run two epilogue sets."""
+    import ctypes
+    lib = _C.load()
+
+    def passes(Q, N, k, d):
+        rows, flags = (ctypes.c_int64 * 64)(), (ctypes.c_int64 * 2)()
+        n = lib.lr_flatip_plan_passes(Q, N, k, d, rows, 16, flags)
+        assert 1 <= n <= 16
+        return [tuple(rows[4 * i:4 * i + 4]) for i in range(n)], tuple(flags)
+
+    for Q in (1, 32, 300, 2304, 10000):
+        for N in (50, 70_000, 1_100_000, 8_800_000):
+            for k in (10, 100, 1000):
+                for d in (64, 128, 512, 768, 1024, 3584, 4096):
+                    ps, (wide, lmul) = passes(Q, N, k, d)
+                    n_tiles = -(-N // 256)
+                    assert ps[0][0] == 0 and ps[-1][1] == n_tiles
+                    for (b0, e0, s0, _), (b1, _e1, _s1, _t1) in zip(ps, ps[1:]):
+                        assert b0 < e0 == b1
+                    for b, e, s, team in ps:
+                        assert 1 <= s <= e - b and team in (0, 1)
+                    assert lmul == (2 if wide else 1)
+                    assert not wide or (d <= 768 and Q > 128 and k <= 352)
+    ps, (wide, lmul) = passes(10000, 1_100_000, 100, 128)   # BASELINE configs[2] on a shard
+    assert [p[:2] for p in ps] == [(0, 128), (128, 512), (512, 2048), (2048, 4297)] and ps[-1][3] == 1 and (wide, lmul) == (1, 2)
+    ps, (wide, _) = passes(10000, 8_800_000, 100, 128)
+    assert [p[:2] for p in ps] == [(0, 128), (128, 512), (512, 2048), (2048, 8192), (8192, 34375)] and wide == 1
+    ps, (wide, _) = passes(10000, 8_800_000, 100, 4096)      # headline: prefix + one main pass on the team schedule
+    assert [p[:2] for p in ps] == [(0, 128), (128, 34375)] and ps[1][3] == 1 and wide == 0
+    assert passes(32, 1_100_000, 100, 3584)[0][0][:3] == (0, 148, 148)   # online: one tile per cluster
