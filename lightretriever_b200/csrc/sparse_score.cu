@@ -50,6 +50,12 @@ struct SSParams {
   uint32_t* floor_q;  // [Q] score floor of each query (k-th best score some unit has proven), zeroed per launch
   uint32_t* next_unit;  // dynamic unit counter, zeroed per launch
   uint32_t* overflow;   // set by the 16-bit pass when an accumulator would exceed 65535; the 32-bit pass runs only then
+  // accumulator passes that follow the bitmap kernel (sparse_score_bitmap_kernel) work through the units it handed back
+  const uint32_t* unit_list;   // null: every unit
+  const uint32_t* unit_count;  // number of entries of unit_list (device memory)
+  // bitmap kernel only: where it records the units it does not finish itself
+  uint32_t* redo_units;
+  uint32_t* redo_count;
 };
 
 // Accumulator access.  AccT = uint16_t packs two documents per shared-memory word (twice the resident warps for the same
@@ -131,12 +137,16 @@ sparse_score_kernel(const SSParams p) {
   for (int i = lane; i < BD; i += 32) acc[i] = 0;
   __syncwarp();
 
-  const uint32_t n_units = uint32_t(p.Q * p.S);
+  const uint32_t n_units = p.unit_list ? ld_relaxed_u32(p.unit_count) : uint32_t(p.Q * p.S);
   for (;;) {
     uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(p.next_unit, 1u);
+    if (lane == 0) {
+      u = atomicAdd(p.next_unit, 1u);
+      if (p.unit_list && u < n_units) u = p.unit_list[u];
+      else if (u >= n_units) u = 0xFFFFFFFFu;
+    }
     u = __shfl_sync(full, u, 0);
-    if (u >= n_units) break;
+    if (u == 0xFFFFFFFFu) break;
     const int64_t q = u / uint32_t(p.S);
     const int s = int(u % uint32_t(p.S));
     const int b0 = int((int64_t(s) * p.nblk) / p.S);
@@ -329,6 +339,231 @@ sparse_score_kernel(const SSParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Bitmap kernel (LR_SPARSE_KERNEL=2): the same warp-granular workers over steps of S2_GROUP blocks (32768 documents),
+// with TWO BITS per document instead of an accumulator.  Most documents a query touches are hit by exactly one of its
+// terms; their score is that one product and needs no accumulator at all.  Pass 1 streams the doc ids of the step and
+// marks `hit`; a second hit of the same document marks `multi` (and counts it).  Pass 2 streams (doc, impact) again
+// (L2 hits): a document without the `multi` bit is scored on the spot and tested against the thresholds; the others are
+// summed in a small open-addressing table (exact: their number is known from pass 1).  8x fewer steps than the
+// accumulator kernel for the same shared memory, so the per-step fixed work (pointer walk, scan, visit set-up) is
+// amortised over ~1000 postings instead of ~130.  Units it does not handle — queries with more than 32 terms, steps
+// with more than S2_HASH_MAX multi-hit documents (dense blocks) — are handed to the accumulator kernel through a list.
+constexpr int S2_GROUP = 8;        // index blocks per step
+constexpr int S2_HASH = 512;       // entries of the multi-hit table (per warp)
+constexpr int S2_HASH_MAX = 384;   // most multi-hit documents a step may have
+
+template <int BD>
+__global__ void __launch_bounds__(SS_MAX_WARPS * 32, 1)
+sparse_score_bitmap_kernel(const SSParams p) {
+  extern __shared__ __align__(16) uint8_t ss_smem[];
+  constexpr int W = BD * S2_GROUP / 32;  // bitmap words
+  const uint32_t full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  uint8_t* wbase = ss_smem + size_t(warp) * p.warp_bytes;
+  uint32_t* hit = reinterpret_cast<uint32_t*>(wbase);
+  uint32_t* multi = hit + W;
+  uint32_t* hkey = multi + W;
+  uint32_t* hval = hkey + S2_HASH;
+  uint64_t* list = reinterpret_cast<uint64_t*>(hval + S2_HASH);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(list + p.cap);
+
+  for (int i = lane; i < 2 * W + 2 * S2_HASH; i += 32) hit[i] = 0;
+  __syncwarp();
+
+  const uint32_t n_units = uint32_t(p.Q * p.S);
+  for (;;) {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(p.next_unit, 1u);
+    u = __shfl_sync(full, u, 0);
+    if (u >= n_units) break;
+    const int64_t q = u / uint32_t(p.S);
+    const int s = int(u % uint32_t(p.S));
+    const int b0 = int((int64_t(s) * p.nblk) / p.S);
+    const int b1 = int((int64_t(s + 1) * p.nblk) / p.S);
+    const int qt0 = p.q_indptr[q];
+    const int nterms = p.q_indptr[q + 1] - qt0;
+    bool handed_back = nterms > 32;  // warp-uniform
+    uint32_t n = 0;                  // entries in `list` (warp-uniform)
+    uint64_t thr = 0xFFFFFFFFull;    // candidates need key > thr; every score-0 key is <= this
+
+    auto append = [&](bool pass, uint64_t key) {
+      uint32_t pm = __ballot_sync(full, pass);
+      while (pm) {
+        const uint32_t room = uint32_t(p.cap) - n;
+        const uint32_t rank = __popc(pm & lt);
+        if (pass && rank < room) {
+          list[n + rank] = key;
+          pass = false;
+        }
+        n += min(uint32_t(__popc(pm)), room);
+        __syncwarp();
+        if (n == uint32_t(p.cap)) {
+          thr = warp_cut_topk(list, &n, p.k, hist);
+          if (p.S > 1 && lane == 0) atomicMax(p.floor_q + q, key_hi(thr));
+          pass = pass && key > thr;
+        }
+        pm = __ballot_sync(full, pass);
+      }
+    };
+
+    if (!handed_back) {
+      const uint32_t* bp_row = nullptr;
+      int64_t post_base = 0;
+      int my_w = 0;
+      uint32_t lo = 0, hi = 0, nxt = 0;
+      if (lane < nterms) {
+        const int t = p.q_tok[qt0 + lane];
+        const int w = p.q_cnt[qt0 + lane];
+        if (t >= 0 && t < p.V && w > 0) {  // terms with a count <= 0 contribute nothing
+          bp_row = p.blockptr + int64_t(t) * (p.nblk + 1);
+          post_base = p.post_indptr[t];
+          my_w = w;
+          lo = bp_row[b0];
+          hi = bp_row[min(b0 + S2_GROUP, b1)];
+          nxt = bp_row[min(b0 + 2 * S2_GROUP, b1)];
+        }
+      }
+      for (int b = b0; b < b1; b += S2_GROUP) {
+        const int d0 = b * BD;
+        const uint32_t floor_s = p.S > 1 ? ld_relaxed_u32(p.floor_q + q) : 0u;
+        int cnt = 0;
+        int64_t start = 0;
+        if (bp_row) {
+          start = post_base + lo;
+          cnt = int(hi - lo);
+          lo = hi;
+          hi = nxt;
+          if (b + 2 * S2_GROUP < b1) nxt = bp_row[min(b + 3 * S2_GROUP, b1)];  // consumed two steps from now
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(full, incl, off);
+          if (lane >= off) incl += t;
+        }
+        const int total = __shfl_sync(full, incl, 31);
+        const int pre = incl - cnt;
+        const int64_t rel = start - pre;  // posting index of flattened position j inside this lane's term = rel + j
+        // largest l in [0, 32) with pre[l] <= j (lanes past the last term hold pre == total > j)
+        auto find_term = [&](int j) {
+          int l = 0;
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int pv = __shfl_sync(full, pre, l + step);
+            if (pv <= j) l += step;
+          }
+          return l;
+        };
+        // ---- pass 1: hit / multi bits
+        uint32_t nmulti = 0;
+        for (int j0 = 0; j0 < total; j0 += 32 * SS_BATCH) {
+          int sl[SS_BATCH];
+#pragma unroll
+          for (int i = 0; i < SS_BATCH; ++i) {
+            sl[i] = -1;
+            if (j0 + i * 32 < total) {  // warp-uniform
+              const int j = min(j0 + i * 32 + lane, total - 1);
+              const int l = find_term(j);
+              const int64_t idx = __shfl_sync(full, rel, l) + j;
+              const int dsl = __ldg(p.post_doc + idx) - d0;
+              if (j0 + i * 32 + lane < total) sl[i] = dsl;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < SS_BATCH; ++i) {
+            if (j0 + i * 32 < total) {
+              bool newm = false;
+              if (sl[i] >= 0) {
+                const uint32_t bit = 1u << (sl[i] & 31);
+                const uint32_t old = atomicOr(&hit[sl[i] >> 5], bit);
+                if (old & bit) newm = (atomicOr(&multi[sl[i] >> 5], bit) & bit) == 0;
+              }
+              nmulti += __popc(__ballot_sync(full, newm));
+            }
+          }
+        }
+        __syncwarp();
+        if (nmulti > uint32_t(S2_HASH_MAX)) {
+          handed_back = true;  // dense step: the accumulator kernel redoes this unit
+        } else {
+          // ---- pass 2: single-hit documents are scored on the spot, multi-hit ones summed in the table
+          for (int j0 = 0; j0 < total; j0 += 32 * SS_BATCH) {
+            int sl[SS_BATCH], add[SS_BATCH];
+#pragma unroll
+            for (int i = 0; i < SS_BATCH; ++i) {
+              sl[i] = 0;
+              add[i] = 0;
+              if (j0 + i * 32 < total) {
+                const int j = min(j0 + i * 32 + lane, total - 1);
+                const int l = find_term(j);
+                const int64_t idx = __shfl_sync(full, rel, l) + j;
+                const int wl = __shfl_sync(full, my_w, l);
+                sl[i] = __ldg(p.post_doc + idx) - d0;
+                add[i] = j0 + i * 32 + lane < total ? wl * int(__ldg(p.post_imp + idx)) : 0;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < SS_BATCH; ++i) {
+              if (j0 + i * 32 < total) {
+                bool cand = false;
+                uint64_t key = 0;
+                if (add[i] > 0) {
+                  if ((multi[sl[i] >> 5] >> (sl[i] & 31)) & 1u) {
+                    const uint32_t kk = uint32_t(sl[i]) + 1u;
+                    uint32_t h = (uint32_t(sl[i]) * 2654435761u) >> 23;  // 9 bits
+                    for (;;) {
+                      const uint32_t old = atomicCAS(&hkey[h], 0u, kk);
+                      if (old == 0u || old == kk) {
+                        atomicAdd(&hval[h], uint32_t(add[i]));
+                        break;
+                      }
+                      h = (h + 1) & (S2_HASH - 1);
+                    }
+                  } else if (uint32_t(add[i]) >= floor_s) {
+                    key = make_key(uint32_t(add[i]), uint32_t(d0 + sl[i]));
+                    cand = key > thr;
+                  }
+                }
+                append(cand, key);
+              }
+            }
+          }
+          __syncwarp();
+          if (nmulti) {
+            for (int h0 = 0; h0 < S2_HASH; h0 += 32) {
+              const uint32_t kk = hkey[h0 + lane];
+              const uint32_t v = hval[h0 + lane];
+              if (kk) {
+                hkey[h0 + lane] = 0;
+                hval[h0 + lane] = 0;
+              }
+              const uint64_t key = make_key(v, uint32_t(d0) + kk - 1u);
+              append(kk != 0u && v > 0u && v >= floor_s && key > thr, key);
+            }
+          }
+        }
+        // ---- clear the bitmaps
+        __syncwarp();
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lane; i < 2 * W / 4; i += 32) reinterpret_cast<uint4*>(hit)[i] = z;
+        __syncwarp();
+        if (handed_back) break;
+      }
+    }
+    if (handed_back) {
+      if (lane == 0) p.redo_units[atomicAdd(p.redo_count, 1u)] = u;
+      continue;
+    }
+    // ---- unit result
+    uint64_t* dst = p.cand + (int64_t(s) * p.Q + q) * p.cap;
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = list[i];
+    if (lane == 0) p.counts[int64_t(s) * p.Q + q] = int32_t(n);
+    __syncwarp();
+  }
+}
+
 __global__ void build_blockptr_kernel(const int64_t* __restrict__ post_indptr, const int32_t* __restrict__ post_doc,
                                       int64_t V, int nblk, int block_docs, uint32_t* __restrict__ blockptr) {
   const int64_t total = V * int64_t(nblk + 1);
@@ -363,12 +598,14 @@ static int ss_env_int(const char* name) {
 }
 static bool ss_batch4() { static const bool v = ss_env_int("LR_SPARSE_BATCH") == 4; return v; }   // sweeps; default 8
 static bool ss_acc32_only() { static const bool v = ss_env_int("LR_SPARSE_ACC") == 32; return v; }  // A/B; default 16 + fallback
+// 2: bitmap kernel first, accumulator kernels for the units it hands back; 1 (default): accumulator kernels only
+static bool ss_bitmap() { static const bool v = ss_env_int("LR_SPARSE_KERNEL") == 2; return v; }
 
 struct SSPlan {
   int bd, nblk, S, cap;
-  int warps[2], warp_bytes[2];  // [0] = 16-bit accumulators, [1] = int32 accumulators
-  int grid[2];
-  size_t smem[2], off_counts, off_floor, off_cand, off_merge, merge_bytes, total_bytes;
+  int warps[3], warp_bytes[3];  // [0] = 16-bit accumulators, [1] = int32 accumulators, [2] = bitmap kernel
+  int grid[3];
+  size_t smem[3], off_counts, off_floor, off_redo, off_cand, off_merge, merge_bytes, total_bytes;
 };
 
 static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
@@ -378,13 +615,14 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   int cap = k + (k / 2 > 156 ? k / 2 : 156);  // k = 100 -> 256
   pl.cap = (cap + 31) / 32 * 32;
   const int G = sm_count();
-  for (int m = 0; m < 2; ++m) {
-    pl.warp_bytes[m] = pl.bd * (m ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2;
+  for (int m = 0; m < 3; ++m) {
+    pl.warp_bytes[m] = m < 2 ? pl.bd * (m ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2
+                             : 2 * (pl.bd * S2_GROUP / 8) + S2_HASH * 8 + pl.cap * 8 + 256 * 4;
     const int warps = int((size_t(227) * 1024 - 1024) / size_t(pl.warp_bytes[m]));
     pl.warps[m] = warps > SS_MAX_WARPS ? SS_MAX_WARPS : warps;
     pl.smem[m] = size_t(pl.warps[m]) * pl.warp_bytes[m];
   }
-  const int64_t slots = int64_t(G) * pl.warps[ss_acc32_only() ? 1 : 0];
+  const int64_t slots = int64_t(G) * pl.warps[ss_bitmap() ? 2 : (ss_acc32_only() ? 1 : 0)];
   // enough units to balance the dynamic hand-out (8 per warp), at most one unit per document block and at most 64
   // lists per query for the merge
   int64_t S = (8 * slots + Q - 1) / Q;
@@ -393,14 +631,15 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   if (S < 1) S = 1;
   pl.S = int(S);
   const int64_t units = Q * S;
-  for (int m = 0; m < 2; ++m) {
+  for (int m = 0; m < 3; ++m) {
     const int64_t ctas = (units + pl.warps[m] - 1) / (pl.warps[m] > 0 ? pl.warps[m] : 1);
     pl.grid[m] = int(ctas < G ? ctas : G);
   }
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   pl.off_counts = 0;
   pl.off_floor = align(size_t(pl.S) * Q * 4);
-  pl.off_cand = align(pl.off_floor + 2 * size_t(Q) * 4 + 256);  // 2 x floor_q [Q], 2 unit counters, the overflow flag
+  pl.off_redo = align(pl.off_floor + 3 * size_t(Q) * 4 + 256);  // 3 x floor_q [Q], 3 unit counters, overflow flag, redo count
+  pl.off_cand = align(pl.off_redo + size_t(units) * 4);          // units handed back by the bitmap kernel
   pl.off_merge = align(pl.off_cand + size_t(pl.S) * Q * pl.cap * 8);
   pl.merge_bytes = topk_merge_scratch_bytes(pl.S, Q, pl.cap, k);
   pl.total_bytes = align(pl.off_merge + pl.merge_bytes);
@@ -481,25 +720,51 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   p.V = V; p.N = N; p.nblk = pl.nblk; p.S = pl.S; p.k = k; p.cap = pl.cap;
   p.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   p.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
-  uint32_t* ctl = reinterpret_cast<uint32_t*>(ws + pl.off_floor);  // floor16 [Q] | floor32 [Q] | next16 | next32 | overflow
-  LR_CUDA(cudaMemsetAsync(ctl, 0, 2 * size_t(Q) * 4 + 12, st));
-  p.overflow = ctl + 2 * Q + 2;
+  // control words: floor [3][Q] (bitmap / 16-bit / int32 pass) | next unit [3] | overflow | redo count
+  uint32_t* ctl = reinterpret_cast<uint32_t*>(ws + pl.off_floor);
+  LR_CUDA(cudaMemsetAsync(ctl, 0, 3 * size_t(Q) * 4 + 5 * 4, st));
+  uint32_t* next3 = ctl + 3 * Q;
+  p.overflow = next3 + 3;
   int rc = LR_OK;
+  if (ss_bitmap()) {
+    p.floor_q = ctl;
+    p.next_unit = next3;
+    p.warp_bytes = pl.warp_bytes[2];
+    p.redo_units = reinterpret_cast<uint32_t*>(ws + pl.off_redo);
+    p.redo_count = next3 + 4;
+    cudaError_t e = cudaFuncSetAttribute(sparse_score_bitmap_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(pl.smem[2]));
+    if (e != cudaSuccess || pl.bd != 4096) {
+      set_error("sparse_score: bitmap kernel unavailable (block_docs %d, %s)", pl.bd, cudaGetErrorString(e));
+      return LR_ECUDA;
+    }
+    sparse_score_bitmap_kernel<4096><<<pl.grid[2], pl.warps[2] * 32, pl.smem[2], st>>>(p);
+    LR_LAUNCH_CHECK();
+    p.unit_list = p.redo_units;   // the accumulator passes below only see what was handed back
+    p.unit_count = p.redo_count;
+  }
   if (!ss_acc32_only()) {
     // optimistic pass with 16-bit accumulators (exact unless a document's score would exceed 65535: flag -> pass 2)
-    p.floor_q = ctl;
-    p.next_unit = ctl + 2 * Q;
+    p.floor_q = ctl + Q;
+    p.next_unit = next3 + 1;
     p.warp_bytes = pl.warp_bytes[0];
     rc = ss_dispatch<uint16_t>(p, pl, st);
     if (rc != LR_OK) return rc;
   } else {
     p.overflow = nullptr;
   }
-  p.floor_q = ctl + Q;
-  p.next_unit = ctl + 2 * Q + 1;
+  p.floor_q = ctl + 2 * Q;
+  p.next_unit = next3 + 2;
   p.warp_bytes = pl.warp_bytes[1];
   rc = ss_dispatch<int32_t>(p, pl, st);  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
   if (rc != LR_OK) return rc;
+  if (ss_env_int("LR_SPARSE_DEBUG")) {  // diagnostics: how much of the batch the bitmap kernel handed back
+    uint32_t host[5] = {0, 0, 0, 0, 0};
+    LR_CUDA(cudaStreamSynchronize(st));
+    LR_CUDA(cudaMemcpy(host, next3, sizeof(host), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "lr_b200 sparse_score: units %lld, handed back %u, 16-bit overflow %u\n", (long long)(Q * pl.S), host[4],
+            host[3]);
+  }
   return topk_merge_two_level(p.cand, p.counts, pl.S, Q, Q, pl.cap, k, LR_SCORE_U32, id_offset, out_scores, out_ids,
                               out_keys, k, ws + pl.off_merge, pl.merge_bytes, st);
 }

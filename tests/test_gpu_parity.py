@@ -679,3 +679,37 @@ def test_online_searcher_graph_replay_matches_eager():
         oracle.check_topk_parity(_np(s), _np(i), ref, k, rtol=1e-2, id_offset=77)
     with pytest.raises(ValueError):
         srv.search(torch.zeros(9 * 32, dtype=torch.long).cuda(), torch.zeros(9, dtype=torch.long).cuda())
+
+
+def test_sparse_score_experimental_bitmap_kernel_is_exact():
+    """LR_SPARSE_KERNEL=2 (experimental, default off; see DESIGN K4): the bitmap kernel with hand-back of dense units and
+    long queries to the accumulator kernels must stay bit-exact.  The switch is read once per process -> subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+import lightretriever_b200 as lr
+from oracle import oracle
+from lightretriever_b200.sparse_search import parse_queries
+rng = np.random.default_rng(3)
+N, V, k = 90000, 3000, 100
+docs = []
+for j in range(N):
+    toks = rng.choice(V, size=int(rng.integers(0, 25)), replace=False)
+    docs.append({str(int(t)): int(rng.integers(1, 400)) for t in toks})
+for j in range(0, N, 2):
+    docs[j]["5"] = int(rng.integers(1, 50))            # head term: dense steps are handed back
+queries = [" ".join(str(int(t)) for t in rng.integers(0, V, size=int(rng.integers(1, 33)))) for _ in range(40)]
+queries += ["5 6 7", "5 5 9 9 9", " ".join(str(t) for t in range(40))]   # head term, repeated terms, > 32 terms
+s = lr.ImpactSearch(vocab_size=V)
+s.index(docs, [str(j) for j in range(N)])
+qd = [oracle.query_counts([int(t) for t in q.split()]) for q in queries]
+es, ei = oracle.impact_topk(qd, [{int(a): b for a, b in d.items()} for d in docs], k)
+gs, gi = s._ensure_index().search_device(*parse_queries(queries, V), k)
+assert (gi.cpu().numpy() == ei).all() and (gs.cpu().numpy() == es).all()
+print("bitmap kernel exact")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LR_SPARSE_KERNEL="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bitmap kernel exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
