@@ -5,6 +5,8 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4-stage ring)
 //   warp 1      MMA issuer     (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16)
 //   warps 2..5  epilogue       (tcgen05.ld 32x32b: one accumulator row per thread)
+//   warps 6..9  second epilogue set (WIDE variant only: short rows, where a tile's epilogue outlasts its MMAs; the two
+//               sets take alternate tiles = alternate accumulator buffers and keep separate candidate lists)
 // The 128x256 f32 accumulator lives in TMEM, double buffered (2 x 256 columns), so the epilogue of
 // tile i overlaps the MMAs of tile i+1.  D = A . B^T with A = [rows, K] and B = [cols, K], both K-major bf16.
 //
