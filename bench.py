@@ -178,7 +178,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step_sample"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(int(args.gpus), 1)),  # the B200 arm's config for the same N
         "cpu_baseline": {k_: cb[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -187,8 +187,8 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "C2@k=100: EmbeddingBag(V=128256,d=%d,bf16) encode + exact IP top-%d, %d-query batches vs %d-doc "
-                        "bf16 corpus" % (args.dim, args.topk, args.queries, args.docs),
+    return {"workload": "C2@k=%d: EmbeddingBag(V=128256,d=%d,bf16) encode + exact IP top-%d, %d-query batches vs %d-doc "
+                        "bf16 corpus" % (args.topk, args.dim, args.topk, args.queries, args.docs),
             "queries_per_step": args.queries, "docs": args.docs, "dim": args.dim, "k": args.topk,
             "max_query_tokens": MAX_TOK, "sharding": f"corpus row-sharded over {world} GPU(s)",
             "l2": "inputs larger than L2 (corpus shard streams from HBM every step)"}
