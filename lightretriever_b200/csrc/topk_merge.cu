@@ -229,7 +229,11 @@ static int merge_launch(MergeParams& p, cudaStream_t st) {
   p.kpad = kpad;
   // staging area: what the longest group can hold, within 48 KB when the grid fills the machine, 192 KB otherwise
   const int64_t group_max = int64_t(p.lists_per_group) * p.cap;
-  const int64_t limit = (p.Q * p.groups >= sm_count()) ? MERGE_STAGE_KEYS : MERGE_STAGE_KEYS_MAX;
+  int64_t limit = (p.Q * p.groups >= sm_count()) ? MERGE_STAGE_KEYS : MERGE_STAGE_KEYS_MAX;
+  // sel [kpad] + stage + ~3 KB of static shared memory must stay within the 227 KB a CTA may own (k > 2048 with the
+  // large staging area would not)
+  const int64_t room = (int64_t(227) * 1024 - 4096 - int64_t(kpad) * 8) / 8;
+  if (limit > room) limit = room;
   p.stage_keys = int(group_max < limit ? group_max : limit);
   const size_t smem = (size_t(kpad) + size_t(p.stage_keys)) * 8;
   cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
