@@ -261,6 +261,20 @@ def test_merge_kernel_exact():
     assert (ei[0] == -1).all()
 
 
+@pytest.mark.parametrize("L,Q,cap,k", [(6, 3, 5000, 4096), (300, 2, 64, 50), (600, 1, 40, 7), (3, 200, 3000, 2048)])
+def test_merge_kernel_shapes_around_the_staging_limits(L, Q, cap, k):
+    """Public lr_topk_merge at the edges of the shared-memory staging: k = 4096 with the large staging area, more lists
+    than the offset table holds (> 512: streaming passes), long lists with a full grid (48 KB staging, streaming)."""
+    rng = np.random.default_rng(L * 7 + k)
+    scores = rng.standard_normal((L, Q, cap)).astype(np.float32)
+    ids = np.stack([rng.permutation(L * cap + 17)[:L * cap].reshape(L, cap) for _ in range(Q)], 1).astype(np.int64)
+    keys = lr.encode_keys(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda())
+    s, i = lr.topk_merge(keys, k)
+    es, ei = oracle.merge_topk(list(scores), list(ids), k)
+    np.testing.assert_array_equal(_np(i), ei)
+    np.testing.assert_array_equal(_np(s), es)
+
+
 # ------------------------------------------------------------------------------------------------ K3
 def test_sparse_head_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "sparse_head.npz"))
