@@ -33,20 +33,27 @@ def ptr(t: torch.Tensor | None) -> int | None:
 
 
 class Workspace:
-    """Grow-only, per-device scratch buffer (256-byte aligned by the caching allocator)."""
+    """Grow-only scratch buffers, one per (device, stream, host thread): the C ABI is re-entrant per (device, stream) and
+    leaves the workspace to the caller, so two streams — or two host threads — must never share one.  Buffers are 256-byte
+    aligned by the caching allocator; a buffer that grows is released in stream order (it was allocated on, and is only
+    used by kernels of, the stream it is keyed by)."""
 
     def __init__(self) -> None:
-        self._buf: dict[torch.device, torch.Tensor] = {}
+        self._buf: dict[tuple, torch.Tensor] = {}
 
     def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        import threading
+
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        buf = self._buf.get(device)
+        key = (device, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+        buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
-            self._buf.pop(device, None)
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self._buf[device] = buf
+            self._buf.pop(key, None)
+            with torch.cuda.device(device):
+                buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._buf[key] = buf
         return buf
 
     def clear(self) -> None:
