@@ -44,6 +44,10 @@ const char* lr_last_error(void);
 int         lr_version(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int         lr_device_sm_count(void);
+/* The LR_* experiment knobs are read from the environment once per thread and the search plans are
+ * cached per shape; call this after changing a knob inside a running process (tests, A/B tools).  No reference
+ * counterpart: the reference re-reads nothing either (its Faiss options are fixed at index build, faiss_index.py:60-70). */
+int         lr_reload_env(void);
 
 /* ---------------------------------------------------------------------------
  * K1  EmbeddingBag query encoder (mean, padding_idx) + MRL truncate + L2 norm
@@ -217,6 +221,11 @@ int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_tok, const in
 int lr_fuse_topk(const float* scores0, const int64_t* ids0, int k0, const float* scores1, const int64_t* ids1, int k1,
                  int64_t Q, int method, double w0, double w1, double eps, double k_rrf,
                  int64_t* out_ids, double* out_scores, int32_t* out_counts, void* stream);
+/* Same with float64 input scores: the dict-shaped callers (fuse_scores_linear / fuse_scores_rrf over
+ * dict[qid -> dict[pid -> float]], score_fuse_utils.py:3-90) hold Python floats, i.e. float64. */
+int lr_fuse_topk_f64(const double* scores0, const int64_t* ids0, int k0, const double* scores1, const int64_t* ids1, int k1,
+                     int64_t Q, int method, double w0, double w1, double eps, double k_rrf,
+                     int64_t* out_ids, double* out_scores, int32_t* out_counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ PROTOTYPES = {
     "lr_last_error": (C.c_char_p, []),
     "lr_version": (_i32, []),
     "lr_device_sm_count": (_i32, []),
+    "lr_reload_env": (_i32, []),
     "lr_embbag_encode": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
     "lr_lasttoken_head": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
     "lr_flatip_workspace_bytes": (_sz, [_i64, _i64, _i32]),
@@ -37,6 +38,8 @@ PROTOTYPES = {
     "lr_encode_keys": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "lr_fuse_topk": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _i32, C.c_double, C.c_double, C.c_double, C.c_double,
                             _vp, _vp, _vp, _vp]),
+    "lr_fuse_topk_f64": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _i32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                _vp, _vp, _vp, _vp]),
     "lr_sparse_head_max": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "lr_sparsify_scratch_bytes": (_sz, [_i64, _i64]),
     "lr_sparsify_quantize": (_i32, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _vp]),
@@ -57,13 +60,20 @@ def load(build_if_missing: bool | None = None) -> C.CDLL:
     if build_if_missing is None:
         build_if_missing = os.environ.get("LR_B200_NO_BUILD", "0") != "1"
     if build_if_missing:
-        try:
-            from . import build as _build
-            if _build.is_stale():
+        from . import build as _build
+        if _build.is_stale():
+            try:
                 _build.build()
-        except Exception as e:  # a stale or missing library without nvcc is fatal below
-            if not LIB_PATH.exists():
-                raise RuntimeError(f"liblr_b200.so is missing and could not be built: {e}") from e
+            except Exception as e:
+                # never run kernels that do not match the sources silently: a stale library is an error unless the
+                # caller explicitly accepts it (LR_B200_ALLOW_STALE=1, e.g. a box without nvcc)
+                if not LIB_PATH.exists():
+                    raise RuntimeError(f"liblr_b200.so is missing and could not be built: {e}") from e
+                if os.environ.get("LR_B200_ALLOW_STALE", "0") != "1":
+                    raise RuntimeError(f"liblr_b200.so is older than its sources and the rebuild failed "
+                                       f"(set LR_B200_ALLOW_STALE=1 to load it anyway): {e}") from e
+                import warnings
+                warnings.warn(f"loading a STALE liblr_b200.so (rebuild failed: {e})", RuntimeWarning)
     if not LIB_PATH.exists():
         raise RuntimeError(
             f"{LIB_PATH} not found: build it with `python -m lightretriever_b200.build` "
@@ -75,6 +85,11 @@ def load(build_if_missing: bool | None = None) -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def reload_env() -> None:
+    """Make the library re-read its LR_* experiment knobs (they are cached after the first call)."""
+    load().lr_reload_env()
 
 
 def last_error() -> str:

@@ -4,6 +4,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <utility>
+
 namespace lr {
 
 static thread_local char g_err[1024] = "";
@@ -33,6 +37,29 @@ int sm_count() {
   return cached[dev];
 }
 
+int ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> have;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return LR_ECUDA;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  int& cur = have[std::make_pair(dev, func)];
+  if (bytes <= cur) return LR_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed: %s", bytes, cudaGetErrorString(e));
+    return LR_ECUDA;
+  }
+  cur = bytes;
+  return LR_OK;
+}
+
+static std::atomic<unsigned> g_env_epoch{1};
+unsigned env_epoch() { return g_env_epoch.load(std::memory_order_acquire); }
+
 ProfileEvents& profile_events() {
   static thread_local ProfileEvents pe;
   return pe;
@@ -44,6 +71,11 @@ extern "C" int lr_set_profile_events(void* ev_begin, void* ev_end) {
   lr::ProfileEvents& pe = lr::profile_events();
   pe.begin = static_cast<cudaEvent_t>(ev_begin);
   pe.end = static_cast<cudaEvent_t>(ev_end);
+  return LR_OK;
+}
+
+extern "C" int lr_reload_env(void) {
+  lr::g_env_epoch.fetch_add(1, std::memory_order_acq_rel);
   return LR_OK;
 }
 

@@ -39,6 +39,16 @@ void set_error(const char* fmt, ...);
 
 int sm_count();  // cached per device
 
+// Raises a kernel's dynamic shared-memory limit to at least `bytes`, once per (device, kernel).  The attribute belongs to
+// the function, not to a stream: setting it per launch with that launch's own size races between host threads (one
+// thread can lower it between another thread's set and launch).  Grow-only under a mutex; callers pass the most the
+// kernel ever needs.  Defined in api.cu.
+int ensure_dyn_smem(const void* func, int bytes);
+
+// Experiment knobs (LR_* environment variables) are read once and cached; lr_reload_env() bumps this epoch so that the
+// caches (and the plan caches keyed on them) are rebuilt — tests flip knobs inside one process.
+unsigned env_epoch();
+
 // ---------------------------------------------------------------- candidate keys
 // A candidate is one u64: high word = order-preserving image of the score, low word =
 // 0xFFFFFFFF - id, so that an unsigned descending sort yields (score desc, id asc).

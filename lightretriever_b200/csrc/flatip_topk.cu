@@ -20,6 +20,37 @@ int topk_merge_two_level(const uint64_t* keys, const int32_t* counts, int L, int
                          int64_t out_key_stride, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t topk_merge_scratch_bytes(int L, int64_t Q, int cap, int k);
 
+// Experiment knobs, read from the environment once (and again after lr_reload_env()); production sets none of them.
+struct FlatipEnv {
+  unsigned epoch = 0;
+  int team_band, cap, cluster, sched, splits, band, wide, prefix_docs, refresh, refresh_growth, biglist, team_window,
+      policy_a, policy_b, debug, krot;
+};
+static const FlatipEnv& flatip_env() {
+  static thread_local FlatipEnv e;
+  const unsigned ep = env_epoch();
+  if (e.epoch != ep) {
+    e.team_band = env_int("LR_FLATIP_TEAM_BAND", 0);
+    e.cap = env_int("LR_FLATIP_CAP", -1);
+    e.cluster = env_int("LR_FLATIP_CLUSTER", 0);
+    e.sched = env_int("LR_FLATIP_SCHED", 1);
+    e.splits = env_int("LR_FLATIP_SPLITS", 0);
+    e.band = env_int("LR_FLATIP_BAND", 32);
+    e.wide = env_int("LR_FLATIP_WIDE", -1);
+    e.prefix_docs = env_int("LR_FLATIP_PREFIX_DOCS", -1);
+    e.refresh = env_int("LR_FLATIP_REFRESH", -1);
+    e.refresh_growth = env_int("LR_FLATIP_REFRESH_GROWTH", 4);
+    e.biglist = env_int("LR_FLATIP_BIGLIST", -1);
+    e.team_window = env_int("LR_FLATIP_TEAM_WINDOW", -1);
+    e.policy_a = env_int("LR_FLATIP_POLICY_A", 0);
+    e.policy_b = env_int("LR_FLATIP_POLICY_B", 0);
+    e.debug = env_int("LR_FLATIP_DEBUG", 0);
+    e.krot = env_int("LR_FLATIP_KROT", 0);
+    e.epoch = ep;
+  }
+  return e;
+}
+
 struct PassPlan {
   int tile_begin, tile_end, splits, units, grid, rounds;
   int sched, band_size, n_bands;  // sched 1: fixed teams per band (band_size groups per full band)
@@ -48,7 +79,7 @@ static bool plan_teams(int m_groups, int nc, int n_tiles_pass, int64_t s_cap, Pa
   double best = -1.0;
   int best_g = 0, best_s = 0;
   int g_hi = m_groups < 20 ? m_groups : 20, g_lo = m_groups < 4 ? m_groups : 4;
-  const int forced_g = env_int("LR_FLATIP_TEAM_BAND", 0);
+  const int forced_g = flatip_env().team_band;
   if (forced_g > 0 && forced_g <= m_groups) g_lo = g_hi = forced_g;
   for (int g = g_lo; g <= g_hi; ++g) {
     if (g > nc) break;
@@ -114,14 +145,15 @@ static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile
   return pp;
 }
 
-static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
+static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used) {
   FlatipPlan pl{};
+  const FlatipEnv& env = flatip_env();
   // Candidate-list capacity.  The running threshold of a row only rises when its list is cut back to the top-k, so
   // between two cuts exactly cap-k entries are admitted and the number of documents consumed grows by cap/k per cut;
   // measured on B200 (profiles/): 2k..2.5k beats both smaller and larger lists.
   int cap = 2 * k > k + 64 ? 2 * k : k + 64;
   if (k <= 128 && cap < 256) cap = 256;
-  cap = env_int("LR_FLATIP_CAP", cap);
+  if (env.cap >= 0) cap = env.cap;
   if (cap < k + 64) cap = k + 64;
   pl.cap = (cap + 63) / 64 * 64;
   // Kernel variant.  Small batches: cluster of 2 with multicast B.  Long lists (k > 352: a list no longer fits the
@@ -130,19 +162,19 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
   // BIGLIST + 256k-document prefix).  Large batches on the team schedule also run as pairs: once the corpus tiles stay
   // L2-resident the halved shared-memory traffic of cta_group::2 is what the power cap rewards (same box, 8.8M x 4096,
   // k=100: 585 ms multicast vs 537 ms pair; profiles/k2_ab_same_box_r1.jsonl).
-  int mode = env_int("LR_FLATIP_CLUSTER", 0);
+  int mode = env.cluster;
   const bool long_lists = pl.cap > LIST_STAGE_ENTRIES;
-  const bool team_sched = env_int("LR_FLATIP_SCHED", 1) != 0 && env_int("LR_FLATIP_SPLITS", 0) == 0 &&
+  const bool team_sched = env.sched != 0 && env.splits == 0 &&
                           (Q + 2 * BM - 1) / (2 * BM) >= 8;
   if (mode == 0 && Q > BM && (long_lists || team_sched)) mode = 3;
-  const GemmGeometry geo = plan_geometry(Q, env_int("LR_FLATIP_BAND", 32), mode);
+  const GemmGeometry geo = plan_geometry(Q, env.band, mode);
   pl.cl = geo.cl; pl.pair = geo.pair; pl.m_groups = geo.m_groups; pl.m_tiles = geo.m_tiles;
   pl.band_size = geo.band_size; pl.n_bands = geo.n_bands; pl.n_clusters = geo.n_clusters;
   pl.n_tiles = int((N + BN - 1) / BN);
   pl.q_pad = int64_t(pl.m_tiles) * BM;
   // Short rows (MRL prefixes): a 128x256 tile needs d_used/16 MMAs of 128 cycles but ~4-5k cycles of one epilogue warp
   // per TMEM lane quarter, so below ~768 columns the epilogue sets the pace: run two epilogue sets on alternate tiles.
-  pl.wide = env_int("LR_FLATIP_WIDE", (d_used <= 768 && Q > BM && !long_lists) ? 1 : 0) != 0 && !long_lists;
+  pl.wide = (env.wide >= 0 ? env.wide : ((d_used <= 768 && Q > BM && !long_lists) ? 1 : 0)) != 0 && !long_lists;
   pl.lmul = pl.wide ? 2 : 1;
   const int64_t list_bytes = pl.q_pad * int64_t(pl.cap) * 8 * pl.lmul;
   const int64_t s_cap = (int64_t(12) << 30) / (list_bytes > 0 ? list_bytes : 1);
@@ -152,7 +184,7 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
   // with perfect thresholds; 4k..8k-document prefixes do not pay for themselves.
   int prefix_tiles = 0;
   int prefix_splits_forced = 0;
-  const int want = env_int("LR_FLATIP_PREFIX_DOCS", -1);
+  const int want = env.prefix_docs;
   if (want != 0) {
     // default prefix: 256 documents per requested result, at least 32768, at most 1/16 of the corpus
     int64_t docs = want > 0 ? want : (int64_t(256) * k > 32768 ? int64_t(256) * k : 32768);
@@ -180,9 +212,9 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
   // of a single main pass take k*N/prefix = 3.4k candidates per query; ranges growing 4x per pass bring that below 1k.
   int main_begin = prefix_tiles;
   pl.n_mid = 0;
-  const int refresh = env_int("LR_FLATIP_REFRESH", d_used <= 1024 ? 1 : 0);
+  const int refresh = env.refresh >= 0 ? env.refresh : (d_used <= 1024 ? 1 : 0);
   if (refresh && prefix_tiles >= 128 && prefix_tiles == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN)) {
-    int growth = env_int("LR_FLATIP_REFRESH_GROWTH", 4);
+    int growth = env.refresh_growth;
     if (growth < 2) growth = 2;
     int64_t len = int64_t(prefix_tiles) * (growth - 1);
     while (pl.n_mid < MAX_MID && main_begin + len + len < pl.n_tiles) {
@@ -194,13 +226,13 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
       len *= growth;
     }
   }
-  pl.main = plan_pass(pl.m_groups, geo.n_clusters, main_begin, pl.n_tiles, s_cap, env_int("LR_FLATIP_SPLITS", 0));
+  pl.main = plan_pass(pl.m_groups, geo.n_clusters, main_begin, pl.n_tiles, s_cap, env.splits);
   pl.main.band_size = pl.band_size;
   pl.main.n_bands = pl.n_bands;
   pl.prefix.band_size = pl.band_size;
   pl.prefix.n_bands = pl.n_bands;
   // Large batches: fixed teams (see plan_teams).  LR_FLATIP_SCHED=0 keeps the round-robin schedule.
-  if (env_int("LR_FLATIP_SCHED", 1) != 0 && pl.cl == 2 && pl.m_groups >= 8 && env_int("LR_FLATIP_SPLITS", 0) == 0) {
+  if (env.sched != 0 && pl.cl == 2 && pl.m_groups >= 8 && env.splits == 0) {
     PassPlan tp = pl.main;
     if (plan_teams(pl.m_groups, geo.n_clusters, pl.n_tiles - main_begin, s_cap, tp)) pl.main = tp;
   }
@@ -224,6 +256,35 @@ static FlatipPlan make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
   if (pm > pl.merge_bytes) pl.merge_bytes = pm;
   pl.total_bytes = align(pl.off_merge + pl.merge_bytes);
   return pl;
+}
+
+// The planner loops (plan_pass: up to 4 x clusters split counts; plan_teams: band widths x multiples) run once per search
+// shape: the online path repeats the same (Q, N, k, d_used) every request.  Per-thread cache, dropped on lr_reload_env().
+static const FlatipPlan& make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
+  struct Entry {
+    int64_t Q, N, d_used;
+    int k, sms;
+    FlatipPlan pl;
+  };
+  constexpr int kEntries = 16;
+  static thread_local Entry cache[kEntries];
+  static thread_local int n_cached = 0, next_slot = 0;
+  static thread_local unsigned epoch = 0;
+  if (epoch != env_epoch()) {
+    n_cached = next_slot = 0;
+    epoch = env_epoch();
+  }
+  const int sms = sm_count();
+  for (int i = 0; i < n_cached; ++i) {
+    const Entry& e = cache[i];
+    if (e.Q == Q && e.N == N && e.k == k && e.d_used == d_used && e.sms == sms) return e.pl;
+  }
+  Entry& e = cache[next_slot];
+  next_slot = (next_slot + 1) % kEntries;
+  if (n_cached < kEntries) ++n_cached;
+  e.Q = Q; e.N = N; e.k = k; e.d_used = d_used; e.sms = sms;
+  e.pl = make_plan_uncached(Q, N, k, d_used);
+  return e.pl;
 }
 
 static thread_local FlatipPlan g_last_plan{};
@@ -252,12 +313,13 @@ static void fill_params(GemmParams& prm, const FlatipPlan& pl, const PassPlan& p
   prm.sched = pp.sched;
   // The window is worth one full-width tile of operand traffic (64 k-blocks): with MRL prefixes (2..16 k-blocks per tile)
   // a one-tile window would make the team counter round trip — not the MMA — the pace of the kernel.
+  const FlatipEnv& env = flatip_env();
   const int auto_window = prm.kblocks >= 64 ? 1 : (64 + prm.kblocks - 1) / prm.kblocks;
-  prm.team_window = env_int("LR_FLATIP_TEAM_WINDOW", auto_window);
-  prm.policy_a = l2_policy(env_int("LR_FLATIP_POLICY_A", 0));
-  prm.policy_b = l2_policy(env_int("LR_FLATIP_POLICY_B", 0));
-  prm.debug_flags = env_int("LR_FLATIP_DEBUG", 0);
-  prm.k_rot = env_int("LR_FLATIP_KROT", 0);
+  prm.team_window = env.team_window >= 0 ? env.team_window : auto_window;
+  prm.policy_a = l2_policy(env.policy_a);
+  prm.policy_b = l2_policy(env.policy_b);
+  prm.debug_flags = env.debug;
+  prm.k_rot = env.krot;
 }
 
 template <int EPI>
@@ -267,7 +329,7 @@ static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorM
   // it is free (4 of 6 stages of 32 KB keep the prefetch depth); for the multicast cluster it costs one of four 48 KB
   // stages, which only pays in short units (k=1000: 129 -> 107 ms at 390 tiles per unit, 810 -> 833 ms at 1427).
   const int tiles_per_unit = (pp.tile_end - pp.tile_begin + pp.splits - 1) / pp.splits;
-  const int big_mode = env_int("LR_FLATIP_BIGLIST", -1);
+  const int big_mode = flatip_env().biglist;
   const bool big = EPI == EPI_TOPK && pl.cap > LIST_STAGE_ENTRIES &&
                    (big_mode == 1 || (big_mode == -1 && (pl.pair || tiles_per_unit < 1000)));
   if (big) {
@@ -373,7 +435,7 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   LR_CHECK_ARG(k >= 1 && k <= 2048, "flatip: k (%d) must be in [1, 2048]", k);
   LR_CHECK_ARG(id_offset >= 0 && id_offset + N <= (int64_t(1) << 32) - 2, "flatip: id_offset + N must stay below 2^32");
   LR_CHECK_ARG(out_scores || out_ids || out_keys, "flatip: no output requested");
-  FlatipPlan pl = make_plan(Q, N, k, d_used);
+  const FlatipPlan& pl = make_plan(Q, N, k, d_used);
   if (!workspace || ws_bytes < pl.total_bytes || (uintptr_t(workspace) & 255)) {
     set_error("flatip: workspace too small or misaligned (%zu given, %zu needed, 256-byte aligned)", ws_bytes,
               pl.total_bytes);
@@ -389,7 +451,7 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   int32_t* counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   const bool two_phase = pl.prefix.units > 0;
-  const int debug = env_int("LR_FLATIP_DEBUG", 0);
+  const int debug = flatip_env().debug;
 
   GemmParams prm{};
   prm.k = k; prm.cap = pl.cap;

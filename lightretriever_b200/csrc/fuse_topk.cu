@@ -18,10 +18,10 @@ namespace lr {
 constexpr int FUSE_THREADS = 256;
 constexpr int FUSE_MAX_SLOTS = 16;  // npad <= 4096
 
-struct FuseParams {
-  const float* s0;
+template <typename ScoreT> struct FuseParams {
+  const ScoreT* s0;
   const int64_t* i0;
-  const float* s1;
+  const ScoreT* s1;
   const int64_t* i1;
   int64_t Q;
   int k0, k1, npad;  // npad = power of two >= k0 + k1
@@ -58,15 +58,17 @@ __device__ __forceinline__ void bitonic_sort_pairs(int64_t* ids, double* val, in
   }
 }
 
-__global__ void __launch_bounds__(FUSE_THREADS) fuse_topk_kernel(const FuseParams p) {
+// ScoreT = float (the searchers' result arrays) or double (dict-shaped callers: Python floats are float64)
+template <typename ScoreT>
+__global__ void __launch_bounds__(FUSE_THREADS) fuse_topk_kernel(const FuseParams<ScoreT> p) {
   extern __shared__ __align__(16) uint8_t fuse_smem[];
   int64_t* ids = reinterpret_cast<int64_t*>(fuse_smem);
   double* val = reinterpret_cast<double*>(ids + p.npad);
-  __shared__ float s_min[2], s_max[2];
+  __shared__ ScoreT s_min[2], s_max[2];
   __shared__ int s_cnt;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  const float* sc[2] = {p.s0 + q * p.k0, p.s1 + q * p.k1};
+  const ScoreT* sc[2] = {p.s0 + q * p.k0, p.s1 + q * p.k1};
   const int64_t* id[2] = {p.i0 + q * p.k0, p.i1 + q * p.k1};
   const int kk[2] = {p.k0, p.k1};
 
@@ -77,18 +79,18 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_topk_kernel(const FuseParam
   }
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  __shared__ float w_mn[FUSE_THREADS / 32], w_mx[FUSE_THREADS / 32];
+  __shared__ ScoreT w_mn[FUSE_THREADS / 32], w_mx[FUSE_THREADS / 32];
   for (int sys = 0; sys < 2; ++sys) {
-    float mn = INFINITY, mx = -INFINITY;
+    ScoreT mn = INFINITY, mx = -INFINITY;
     for (int i = tid; i < kk[sys]; i += FUSE_THREADS)
       if (id[sys][i] >= 0) {
-        mn = fminf(mn, sc[sys][i]);
-        mx = fmaxf(mx, sc[sys][i]);
+        mn = min(mn, sc[sys][i]);
+        mx = max(mx, sc[sys][i]);
       }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off));
-      mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
+      mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off));
+      mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
     }
     if ((tid & 31) == 0) {
       w_mn[tid >> 5] = mn;
@@ -96,10 +98,10 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_topk_kernel(const FuseParam
     }
     __syncthreads();
     if (tid == 0) {
-      float a = INFINITY, b = -INFINITY;
+      ScoreT a = INFINITY, b = -INFINITY;
       for (int w = 0; w < FUSE_THREADS / 32; ++w) {
-        a = fminf(a, w_mn[w]);
-        b = fmaxf(b, w_mx[w]);
+        a = min(a, w_mn[w]);
+        b = max(b, w_mx[w]);
       }
       s_min[sys] = a;
       s_max[sys] = b;
@@ -182,13 +184,14 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_topk_kernel(const FuseParam
 
 using namespace lr;
 
-extern "C" int lr_fuse_topk(const float* scores0, const int64_t* ids0, int k0, const float* scores1, const int64_t* ids1,
-                            int k1, int64_t Q, int method, double w0, double w1, double eps, double k_rrf,
-                            int64_t* out_ids, double* out_scores, int32_t* out_counts, void* stream) {
+template <typename ScoreT>
+static int fuse_launch(const ScoreT* scores0, const int64_t* ids0, int k0, const ScoreT* scores1, const int64_t* ids1, int k1,
+                       int64_t Q, int method, double w0, double w1, double eps, double k_rrf, int64_t* out_ids,
+                       double* out_scores, int32_t* out_counts, void* stream) {
   LR_CHECK_ARG(scores0 && ids0 && scores1 && ids1 && out_ids && out_scores, "fuse_topk: null pointer");
   LR_CHECK_ARG(Q >= 1 && k0 >= 1 && k1 >= 1 && k0 + k1 <= 4096, "fuse_topk: need Q >= 1 and 2 <= k0 + k1 <= 4096");
   LR_CHECK_ARG(method == 0 || method == 1, "fuse_topk: method must be 0 (linear) or 1 (rrf)");
-  FuseParams p{};
+  FuseParams<ScoreT> p{};
   p.s0 = scores0; p.i0 = ids0; p.s1 = scores1; p.i1 = ids1; p.Q = Q; p.k0 = k0; p.k1 = k1;
   int npad = 2;
   while (npad < k0 + k1) npad <<= 1;
@@ -196,12 +199,23 @@ extern "C" int lr_fuse_topk(const float* scores0, const int64_t* ids0, int k0, c
   p.method = method; p.w0 = w0; p.w1 = w1; p.eps = eps; p.k_rrf = k_rrf;
   p.out_ids = out_ids; p.out_scores = out_scores; p.out_counts = out_counts;
   const size_t smem = size_t(npad) * 16;
-  cudaError_t e = cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
-    return LR_ECUDA;
-  }
-  fuse_topk_kernel<<<unsigned(Q), FUSE_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(fuse_topk_kernel<ScoreT>), 4096 * 16);  // the k0 + k1 <= 4096 maximum, once
+  if (rc) return rc;
+  fuse_topk_kernel<ScoreT><<<unsigned(Q), FUSE_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   LR_LAUNCH_CHECK();
   return LR_OK;
+}
+
+extern "C" int lr_fuse_topk(const float* scores0, const int64_t* ids0, int k0, const float* scores1, const int64_t* ids1,
+                            int k1, int64_t Q, int method, double w0, double w1, double eps, double k_rrf,
+                            int64_t* out_ids, double* out_scores, int32_t* out_counts, void* stream) {
+  return fuse_launch<float>(scores0, ids0, k0, scores1, ids1, k1, Q, method, w0, w1, eps, k_rrf, out_ids, out_scores,
+                            out_counts, stream);
+}
+
+extern "C" int lr_fuse_topk_f64(const double* scores0, const int64_t* ids0, int k0, const double* scores1,
+                                const int64_t* ids1, int k1, int64_t Q, int method, double w0, double w1, double eps,
+                                double k_rrf, int64_t* out_ids, double* out_scores, int32_t* out_counts, void* stream) {
+  return fuse_launch<double>(scores0, ids0, k0, scores1, ids1, k1, Q, method, w0, w1, eps, k_rrf, out_ids, out_scores,
+                             out_counts, stream);
 }

@@ -674,12 +674,8 @@ extern "C" size_t lr_sparse_score_workspace_bytes(int64_t Q, int64_t N, int k) {
 template <int BD, int NB, typename AccT>
 static int ss_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
   const int m = sizeof(AccT) == 4 ? 1 : 0;
-  cudaError_t e = cudaFuncSetAttribute(sparse_score_kernel<BD, NB, AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(pl.smem[m]));
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", pl.smem[m], cudaGetErrorString(e));
-    return LR_ECUDA;
-  }
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_kernel<BD, NB, AccT>), 227 * 1024);
+  if (rc) return rc;
   sparse_score_kernel<BD, NB, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
   LR_LAUNCH_CHECK();
   return LR_OK;
@@ -732,12 +728,11 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
     p.warp_bytes = pl.warp_bytes[2];
     p.redo_units = reinterpret_cast<uint32_t*>(ws + pl.off_redo);
     p.redo_count = next3 + 4;
-    cudaError_t e = cudaFuncSetAttribute(sparse_score_bitmap_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(pl.smem[2]));
-    if (e != cudaSuccess || pl.bd != 4096) {
-      set_error("sparse_score: bitmap kernel unavailable (block_docs %d, %s)", pl.bd, cudaGetErrorString(e));
+    if (pl.bd != 4096) {
+      set_error("sparse_score: bitmap kernel needs block_docs 4096 (got %d)", pl.bd);
       return LR_ECUDA;
     }
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_bitmap_kernel<4096>), 227 * 1024))) return rc;
     sparse_score_bitmap_kernel<4096><<<pl.grid[2], pl.warps[2] * 32, pl.smem[2], st>>>(p);
     LR_LAUNCH_CHECK();
     p.unit_list = p.redo_units;   // the accumulator passes below only see what was handed back

@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergePa
     }
     __syncthreads();
     staged = s_total <= uint32_t(p.stage_keys);
+    // every thread has read s_total before anyone may overwrite it below (the unstaged path resets it)
+    __syncthreads();
   }
   // iterate over every candidate of this (query, group); f(key).  Empty slots (key 0) are skipped.
   auto for_each_candidate = [&](auto&& f) {
@@ -94,7 +96,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergePa
     } else {
       for (int l = warp; l < nl; l += MERGE_THREADS / 32) {
         const int64_t list = int64_t(l0 + l) * p.q_stride + q;
-        const int n = p.counts ? p.counts[list] : p.cap;
+        int n = p.counts ? p.counts[list] : p.cap;
+        n = n < 0 ? 0 : (n > p.cap ? p.cap : n);  // same clamp as the staged path: a bad count never reads past its list
         const uint64_t* src = p.keys + list * p.cap;
         for (int i = lane; i < n; i += 32) {
           const uint64_t key = src[i];
@@ -119,8 +122,6 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergePa
   }
   uint32_t total;
   {
-    if (tid == 0) s_total = staged ? s_total : 0u;
-    __syncthreads();
     uint32_t local = 0;
     for_each_candidate([&](uint64_t) { ++local; });
     __syncthreads();
@@ -236,11 +237,9 @@ static int merge_launch(MergeParams& p, cudaStream_t st) {
   if (limit > room) limit = room;
   p.stage_keys = int(group_max < limit ? group_max : limit);
   const size_t smem = (size_t(kpad) + size_t(p.stage_keys)) * 8;
-  cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(topk_merge, %zu) failed: %s", smem, cudaGetErrorString(e));
-    return LR_ECUDA;
-  }
+  // the most this kernel ever asks for (sel + the large staging area, within what a CTA may own), set once per device
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(topk_merge_kernel), 227 * 1024 - 4096);
+  if (rc) return rc;
   topk_merge_kernel<<<unsigned(p.Q * p.groups), MERGE_THREADS, smem, st>>>(p);
   LR_LAUNCH_CHECK();
   return LR_OK;

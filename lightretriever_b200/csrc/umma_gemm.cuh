@@ -234,6 +234,9 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
 }
 
 constexpr float BF16_LOWEST = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
+// Longest a producer waits for its team (about 2-3 ms; a full-width tile takes ~30k cycles, so a live team is never this
+// far apart).  After one timeout the cluster stops pacing itself for the rest of the launch.
+constexpr long long TEAM_WAIT_CYCLES = 4ll * 1000 * 1000;
 
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs own adjacent row tiles of the same column split; each
 // loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, so the L2 -> SM
@@ -312,6 +315,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int team_slot = -1, ti = 0;  // progress counter in use and tiles issued against it (cumulative over the units)
+      // The team pacing is a performance hint (L2 reuse of B tiles), never a data dependency: a member that does not show
+      // up within TEAM_WAIT_CYCLES (its SM is held by another kernel, MPS, a smaller part) ends the pacing for this
+      // cluster — it runs free for the rest of the launch instead of waiting on a CTA that may not be resident.
+      bool team_live = true;
       for_each_unit(p, cluster_id, n_clusters, [&](int m_group, int split, int team_size, int ctr_index) {
         int64_t c0, c1;
         int m_tile = m_group * CL + cta_rank;  // may be a padding tile (>= m_tiles): TMA zero-fills it
@@ -328,15 +335,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ti = 0;
         }
         for (int64_t cb = c0; cb < c1; cb += BN, ++ti) {
-          if (team_sync && ti >= p.team_window) {
+          if (team_sync && team_live && ti >= p.team_window) {
             // do not run more than team_window tiles ahead of the slowest member of the team
             const uint32_t need = uint32_t(team_size) * uint32_t(ti - p.team_window + 1);
             if (ld_acquire_u32(ctr) < need) {
               const long long t0 = clock64();
               while (ld_acquire_u32(ctr) < need) {
-                if (clock64() - t0 > LR_MBAR_TIMEOUT_CYCLES) {
-                  printf("lr_b200: team barrier timeout block %d split %d tile %d\n", blockIdx.x, split, ti);
-                  __trap();
+                if (clock64() - t0 > TEAM_WAIT_CYCLES) {
+                  team_live = false;
+                  break;
                 }
               }
             }
@@ -736,11 +743,9 @@ template <int EPI, int CL, bool PAIR = false, bool BIGLIST = false, bool WIDE = 
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
   auto kern = umma_gemm_kernel<EPI, CL, PAIR, BIGLIST, WIDE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_TOTAL, cudaGetErrorString(e));
-    return LR_ECUDA;
-  }
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), GEMM_SMEM_TOTAL);
+  if (rc) return rc;
+  cudaError_t e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(grid));
   cfg.blockDim = dim3(WIDE ? GEMM_THREADS_WIDE : GEMM_THREADS);
@@ -753,9 +758,34 @@ inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // The team schedule only pays when the whole grid is co-resident (one cluster per SM pair).  On a device where fewer
+  // clusters fit (a smaller part, MPS with an SM limit) the same units are walked round robin instead: the unit set
+  // (row group x split) and the candidate-list layout do not depend on the schedule.
+  GemmParams prm_rr;
+  const GemmParams* pp = &prm;
+  if (prm.sched != 0) {
+    static int max_clusters[64];  // per device, this kernel instance; 0 = not queried yet
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+      if (max_clusters[dev] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+          cudaGetLastError();
+          n = -1;  // unknown: trust the plan (the in-kernel wait is bounded either way)
+        }
+        max_clusters[dev] = n;
+      }
+      if (max_clusters[dev] > 0 && max_clusters[dev] * CL < grid) {
+        prm_rr = prm;
+        prm_rr.sched = 0;
+        pp = &prm_rr;
+      }
+    }
+  }
   ProfileEvents& pe = profile_events();
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.begin, st));
-  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, prm);
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, *pp);
   if (e != cudaSuccess) {
     set_error("kernel launch failed: %s (grid=%d cluster=%d)", cudaGetErrorString(e), grid, CL);
     return LR_ECUDA;

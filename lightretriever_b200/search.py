@@ -6,7 +6,11 @@ Mirrors
   * ``FlatIPFaissSearch`` / ``DenseRetrievalFaissSearch`` (retriever/faiss_search.py:46-293, 477-510):
     ``index(corpus_emb, corpus_ids)``, ``retrieve_with_emb(query_emb, query_ids, top_k)``, ``_clear()``, ``search``.
 The corpus lives in HBM as bf16 rows; scoring + top-k is one fused tcgen05 kernel plus a merge
-(csrc/umma_gemm.cuh, csrc/topk_merge.cu).  Differences from Faiss that are part of the contract:
+(csrc/umma_gemm.cuh, csrc/topk_merge.cu).  Results are device arrays first: a search yields sorted candidate keys
+``[Q, k]`` (u64 = order-preserving score << 32 | ~id); chunk loops and shards combine them with ``lr_topk_merge`` and the
+reference's nested dicts are built once, at the end, by ``arrays_to_dict``.  With ``use_multiple_gpu=True`` under an
+initialised ``torch.distributed`` group every rank keeps one row shard (``sharded.ShardedFlatIPIndex``, the counterpart
+of Faiss ``shard=True``, faiss_index.py:60-70).  Differences from Faiss that are part of the contract:
   * equal scores are ordered by ascending id (Faiss: unspecified);
   * when fewer than k documents exist the tail is (score -inf, id -1) and is dropped from result dicts
     (the reference lets numpy wrap id -1 to the last passage, SURVEY §8c trap 8).
@@ -14,8 +18,8 @@ The corpus lives in HBM as bf16 rows; scoring + top-k is one fused tcgen05 kerne
 from __future__ import annotations
 
 import csv
-import heapq
 import logging
+import struct
 import os
 import time
 from typing import Optional, Sequence
@@ -122,6 +126,32 @@ def encode_keys(scores: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     return keys
 
 
+def decode_keys(keys: torch.Tensor, score_kind: int = _C.LR_SCORE_F32):
+    """Sorted candidate keys [Q, k] -> (scores f32 [Q, k], ids i64 [Q, k]); empty slots become (-inf, -1)."""
+    return topk_merge(keys.unsqueeze(0).contiguous(), keys.shape[1], score_kind=score_kind)
+
+
+def merge_keys(key_lists: Sequence[torch.Tensor], k: int, score_kind: int = _C.LR_SCORE_F32) -> torch.Tensor:
+    """Exact top-k (as sorted keys [Q, k]) of the union of several per-query key lists [Q, k_i] with global ids: the
+    device form of the reference's heap merge (hybrid_search.py:182-205).  Lists may have different widths."""
+    width = max(t.shape[1] for t in key_lists)
+    stack = torch.zeros((len(key_lists), key_lists[0].shape[0], width), dtype=torch.int64, device=key_lists[0].device)
+    for l, t in enumerate(key_lists):
+        stack[l, :, :t.shape[1]] = t
+    return topk_merge(stack, k, score_kind=score_kind, return_keys=True)[2]
+
+
+def drop_identical(keys: torch.Tensor, self_pos: torch.Tensor) -> torch.Tensor:
+    """`ignore_identical_ids` (hybrid_search.py:193): the candidate whose id equals the query's own corpus position
+    (self_pos [Q] i64, -1 = the query is not a corpus document) becomes an empty slot."""
+    ids = 0xFFFFFFFF - (keys & 0xFFFFFFFF)
+    return torch.where((ids == self_pos.to(keys.device)[:, None]) & (keys != 0), torch.zeros_like(keys), keys)
+
+
+_FAISS_FLAT_IP = 0x49467849  # fourcc("IxFI")
+_FAISS_HEADER = struct.Struct("<Iiqqq?iQ")  # fourcc, d, ntotal, dummy, dummy, is_trained, metric_type, n_floats
+
+
 class FlatIPIndex:
     """HBM-resident flat inner-product index with the ``FaissIndex`` surface (faiss_index.py:20-73)."""
 
@@ -129,10 +159,22 @@ class FlatIPIndex:
                  device: Optional[torch.device] = None, id_offset: int = 0):
         self.dim = dim
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self._chunks: list[torch.Tensor] = []
-        self._corpus: Optional[torch.Tensor] = None
+        self._buf: Optional[torch.Tensor] = None  # [capacity, dim] bf16; rows [0, _n) are filled
+        self._n = 0
         self._passage_ids = None if passage_ids is None else np.asarray(passage_ids, dtype=np.int64)
         self.id_offset = int(id_offset)
+
+    def reserve(self, n_rows: int) -> None:
+        """Size the resident buffer up front so that ``add`` copies every chunk straight into place: no concatenation
+        and no second copy of the shard (a 72 GB corpus must not peak at 144 GB)."""
+        if self.dim is None:
+            raise ValueError("reserve() needs the dimension")
+        if self._buf is not None and self._buf.shape[0] >= n_rows:
+            return
+        new = torch.empty((int(n_rows), self.dim), dtype=torch.bfloat16, device=self.device)
+        if self._n:
+            new[:self._n] = self._buf[:self._n]
+        self._buf = new
 
     # faiss.IndexFlatIP.add
     def add(self, emb) -> None:
@@ -143,38 +185,47 @@ class FlatIPIndex:
             self.dim = t.shape[1]
         if t.shape[1] != self.dim:
             raise ValueError(f"dimension mismatch: index {self.dim}, got {t.shape[1]}")
-        self._chunks.append(t.to(device=self.device, dtype=torch.bfloat16, non_blocking=True))
-        self._corpus = None
+        need = self._n + t.shape[0]
+        if self._buf is None or self._buf.shape[0] < need:  # not reserved: grow geometrically (amortised copies)
+            self.reserve(max(need, 2 * self._n))
+        self._buf[self._n:need].copy_(t, non_blocking=True)  # dtype conversion (-> bf16) happens in the copy
+        self._n = need
 
     @property
     def ntotal(self) -> int:
-        return sum(c.shape[0] for c in self._chunks)
+        return self._n
 
     @property
     def corpus(self) -> torch.Tensor:
-        if self._corpus is None:
-            if not self._chunks:
-                raise RuntimeError("index is empty")
-            self._corpus = self._chunks[0] if len(self._chunks) == 1 else torch.cat(self._chunks, dim=0)
-            self._chunks = [self._corpus]
-        return self._corpus
+        if self._n == 0:
+            raise RuntimeError("index is empty")
+        return self._buf[:self._n]
 
     @classmethod
     def build(cls, passage_ids: Sequence[int], passage_embeddings, index: Optional["FlatIPIndex"] = None,
               buffer_size: int = 50000) -> "FlatIPIndex":
         if index is None:
             index = cls(passage_embeddings.shape[1])
+        if index.dim is None:
+            index.dim = passage_embeddings.shape[1]
+        index.reserve(index.ntotal + len(passage_ids))
         for start in range(0, len(passage_ids), buffer_size):
             index.add(passage_embeddings[start:start + buffer_size])
         index._passage_ids = np.asarray(passage_ids, dtype=np.int64)
         return index
 
-    def search_device(self, query_embeddings: torch.Tensor, k: int, d_used: Optional[int] = None, **kw):
+    def _query(self, query_embeddings) -> torch.Tensor:
         q = query_embeddings
         if not isinstance(q, torch.Tensor):
             q = torch.from_numpy(np.ascontiguousarray(q))
-        q = q.to(device=self.device, dtype=torch.bfloat16, non_blocking=True)
-        return flatip_topk(q, self.corpus, k, d_used=d_used, id_offset=self.id_offset, **kw)
+        return q.to(device=self.device, dtype=torch.bfloat16, non_blocking=True)
+
+    def search_device(self, query_embeddings, k: int, d_used: Optional[int] = None, **kw):
+        return flatip_topk(self._query(query_embeddings), self.corpus, k, d_used=d_used, id_offset=self.id_offset, **kw)
+
+    def search_keys(self, query_embeddings, k: int, d_used: Optional[int] = None) -> torch.Tensor:
+        """Sorted candidate keys [Q, k] with ids offset by ``id_offset`` (what shards and chunk loops exchange)."""
+        return self.search_device(query_embeddings, k, d_used=d_used, return_keys=True)[2]
 
     def search(self, query_embeddings, k: int, **kwargs) -> tuple[np.ndarray, np.ndarray]:
         num_queries = query_embeddings.shape[0]
@@ -191,21 +242,60 @@ class FlatIPIndex:
                     num_queries / max(total_time, 1e-9))
         return scores_arr, ids_arr
 
-    def to_gpu(self):
-        return self  # already HBM-resident
+    def to_gpu(self, group=None):
+        """faiss_index.py:60-70.  The rows are already in HBM; under an initialised process group with more than one rank
+        the index becomes this rank's shard of a ``ShardedFlatIPIndex`` (the counterpart of Faiss ``shard=True``): every
+        rank must hold the same rows when calling this, and each keeps ``[lo, hi)``."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self
+        from .sharded import ShardedFlatIPIndex
+
+        sh = ShardedFlatIPIndex(self.dim, self.ntotal, device=self.device, group=group, id_base=self.id_offset)
+        sh.add_local(self.corpus[sh.lo:sh.hi])
+        sh._passage_ids = self._passage_ids
+        self.reset()
+        return sh
 
     def reset(self) -> None:
-        self._chunks = []
-        self._corpus = None
+        self._buf = None
+        self._n = 0
 
-    def save(self, fname: str) -> None:
-        torch.save({"corpus": self.corpus.cpu(), "passage_ids": self._passage_ids, "id_offset": self.id_offset}, fname)
+    # ---- persistent format: the file faiss.write_index writes for an IndexFlatIP (faiss_index.py:42-43,
+    #      faiss_search.py:113-123, 477-488): fourcc "IxFI", d, ntotal, two dummies, is_trained, metric_type (0 = inner
+    #      product), then the row-major fp32 vectors as a length-prefixed array.  Restated from Faiss's index_write.cpp
+    #      (Faiss itself is not installed here: the round trip below is self-consistent, not pinned against Faiss).
+    def save(self, fname: str, rows_per_write: int = 1 << 16) -> None:
+        n, d = self.ntotal, int(self.dim)
+        with open(fname, "wb") as f:
+            f.write(_FAISS_HEADER.pack(_FAISS_FLAT_IP, d, n, 1 << 20, 1 << 20, True, 0, n * d))
+            for lo in range(0, n, rows_per_write):
+                f.write(self._buf[lo:min(lo + rows_per_write, n)].float().cpu().numpy().tobytes())
 
     @classmethod
-    def load(cls, fname: str, device: Optional[torch.device] = None) -> "FlatIPIndex":
-        blob = torch.load(fname, map_location="cpu", weights_only=False)
-        idx = cls(blob["corpus"].shape[1], blob["passage_ids"], device=device, id_offset=blob.get("id_offset", 0))
-        idx.add(blob["corpus"])
+    def load(cls, fname: str, passage_ids: Optional[Sequence[int]] = None, device: Optional[torch.device] = None,
+             rows: Optional[tuple[int, int]] = None, id_offset: int = 0, rows_per_read: int = 1 << 16) -> "FlatIPIndex":
+        """Read a Faiss ``IndexFlatIP`` file straight into HBM (fp32 on disk -> bf16 rows), optionally only the row range
+        ``rows = (lo, hi)`` — a rank's shard of a reference-built index."""
+        with open(fname, "rb") as f:
+            hdr = f.read(_FAISS_HEADER.size)
+        if len(hdr) < _FAISS_HEADER.size:
+            raise ValueError(f"{fname}: too short for a Faiss index")
+        fourcc, d, n, _, _, _, metric, n_floats = _FAISS_HEADER.unpack(hdr)
+        if fourcc != _FAISS_FLAT_IP or metric != 0:
+            raise ValueError(f"{fname}: not a Faiss IndexFlatIP file (fourcc {fourcc:#x}, metric {metric}); only the exact "
+                             "inner-product index is on the hot path")
+        if d <= 0 or n < 0 or n_floats != n * d:
+            raise ValueError(f"{fname}: inconsistent header (d={d}, ntotal={n}, floats={n_floats})")
+        lo, hi = (0, n) if rows is None else rows
+        if not 0 <= lo <= hi <= n:
+            raise ValueError(f"row range {rows} outside [0, {n}]")
+        data = np.memmap(fname, dtype=np.float32, mode="r", offset=_FAISS_HEADER.size, shape=(n, d))
+        idx = cls(d, passage_ids, device=device, id_offset=id_offset)
+        idx.reserve(hi - lo)
+        for a in range(lo, hi, rows_per_read):
+            idx.add(np.ascontiguousarray(data[a:min(a + rows_per_read, hi)]))
         return idx
 
 
@@ -229,8 +319,28 @@ def load_tsv_to_dict(input_path: str, header: bool = True) -> dict:
     return mappings
 
 
+def sorted_corpus(corpus: dict) -> tuple[list, list]:
+    """Longest document first, the order every reference searcher walks a dict corpus in (faiss_search.py:209-212)."""
+    ids = sorted(corpus, key=lambda c: len(corpus[c].get("text", "")) if isinstance(corpus[c], dict) else len(corpus[c]),
+                 reverse=True)
+    return ids, [corpus[c] for c in ids]
+
+
+def rows_to_dict(scores: torch.Tensor, ids: torch.Tensor, query_ids: Sequence, names, keep_empty: bool = True) -> dict:
+    """(scores [Q, k], ids [Q, k] with -1 padding) -> ``dict[qid -> dict[name(id) -> float]]``, built in one pass over
+    host copies.  ``names`` maps a document position to its corpus id (a sequence, or a callable)."""
+    s, i = scores.cpu().numpy(), ids.cpu().numpy()
+    look = names if callable(names) else names.__getitem__
+    out = {}
+    for r, qid in enumerate(query_ids):
+        row = {look(doc): sc for doc, sc in zip(i[r].tolist(), s[r].tolist()) if doc >= 0}
+        if row or keep_empty:
+            out[qid] = row
+    return out
+
+
 class FlatIPSearch:
-    """``FlatIPFaissSearch`` surface (faiss_search.py:46-293, 477-510) over ``FlatIPIndex``."""
+    """``FlatIPFaissSearch`` surface (faiss_search.py:46-293, 477-510) over ``FlatIPIndex`` / ``ShardedFlatIPIndex``."""
 
     def __init__(self, model=None, batch_size: int = 128, corpus_chunk_size: Optional[int] = None,
                  use_single_gpu: bool = False, use_multiple_gpu: bool = False, **kwargs):
@@ -240,9 +350,13 @@ class FlatIPSearch:
         self.show_progress_bar = kwargs.get("show_progress_bar", True)
         self.convert_to_tensor = kwargs.get("convert_to_tensor", True)
         self.mapping_tsv_keys = ["beir-docid", "faiss-docid"]
-        self.faiss_index: Optional[FlatIPIndex] = None
+        self.faiss_index = None
+        # The corpus always lives in HBM, so `use_single_gpu` changes nothing; `use_multiple_gpu` shards it over the ranks
+        # of `group` (one process per GPU) when torch.distributed is initialised, as Faiss shard=True does over the
+        # visible devices of one process (faiss_search.py:480-504).
         self.use_single_gpu = use_single_gpu
         self.use_multiple_gpu = use_multiple_gpu
+        self.group = kwargs.get("group", None)
         self.dim_size = None
         self.mapping: dict = {}
         self.rev_mapping: dict = {}
@@ -264,116 +378,129 @@ class FlatIPSearch:
     def encode_corpus(self, corpus, batch_size: int, **kwargs):
         return self.model.encode_corpus(corpus=corpus, batch_size=batch_size, **kwargs)
 
+    def _world(self) -> int:
+        import torch.distributed as dist
+
+        if self.use_multiple_gpu and dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
     def _create_mapping_ids(self, corpus_ids):
         if not all(isinstance(doc_id, int) for doc_id in corpus_ids):
-            for idx in range(len(corpus_ids)):
-                self.mapping[corpus_ids[idx]] = idx
-                self.rev_mapping[idx] = corpus_ids[idx]
+            self.mapping = {cid: idx for idx, cid in enumerate(corpus_ids)}
+            self.rev_mapping = dict(enumerate(corpus_ids))
 
     def _clear(self):
         if self.faiss_index is not None:
             self.faiss_index.reset()
-            del self.faiss_index
         self.faiss_index = None
         self.dim_size = None
         self.mapping = {}
         self.rev_mapping = {}
 
+    def _build_index(self, corpus_emb, passage_ids, id_base: int = 0):
+        """Resident index over `corpus_emb` whose result ids start at `id_base`; a row shard per rank when sharded."""
+        if self._world() > 1:
+            from .sharded import ShardedFlatIPIndex
+
+            sh = ShardedFlatIPIndex(corpus_emb.shape[1], corpus_emb.shape[0], device=self.device, group=self.group,
+                                    id_base=id_base)
+            sh.add_local(corpus_emb[sh.lo:sh.hi])
+            sh._passage_ids = None if passage_ids is None else np.asarray(passage_ids, dtype=np.int64)
+            return sh
+        return FlatIPIndex.build(passage_ids, corpus_emb, FlatIPIndex(corpus_emb.shape[1], device=self.device,
+                                                                     id_offset=id_base))
+
     def index(self, corpus_emb, corpus_ids: Sequence[str]):
         self._create_mapping_ids(corpus_ids)
         self.dim_size = corpus_emb.shape[1]
-        faiss_ids = [self.mapping.get(cid) for cid in corpus_ids] if self.mapping else list(corpus_ids)
-        if self.mapping:
-            passage_ids = faiss_ids
-        else:
-            passage_ids = [int(c) for c in corpus_ids]
-        base = FlatIPIndex(self.dim_size, device=self.device)
-        self.faiss_index = FlatIPIndex.build(passage_ids, corpus_emb, base)
-
-    def retrieve_with_emb(self, query_emb, query_ids: Sequence[str], top_k: int, **kwargs) -> dict:
-        if self.faiss_index is None:
-            raise RuntimeError("index() must be called before retrieve_with_emb()")
-        scores_arr, ids_arr = self.faiss_index.search(query_emb, top_k, **kwargs)
-        results: dict[str, dict[str, float]] = {}
-        for i in range(len(query_ids)):
-            row = {}
-            for doc_id, score in zip(ids_arr[i].tolist(), scores_arr[i].tolist()):
-                if doc_id < 0:
-                    continue  # fewer than k documents: (-inf, -1) padding is dropped
-                row[self.rev_mapping[doc_id] if self.rev_mapping else str(doc_id)] = float(score)
-            results[query_ids[i]] = row
-        return results
+        passage_ids = list(range(len(corpus_ids))) if self.mapping else [int(c) for c in corpus_ids]
+        self.faiss_index = self._build_index(corpus_emb, passage_ids)
 
     def retrieve_arrays(self, query_emb, top_k: int, **kwargs):
-        """Device arrays (scores f32 [Q,k], doc positions i64 [Q,k], -1 padded): the f2 row — results stay on device and
-        are turned into the reference's nested dicts only when a caller asks for them (`arrays_to_dict`)."""
+        """Device arrays (scores f32 [Q,k], doc positions i64 [Q,k], -1 padded): results stay on device and become the
+        reference's nested dicts only when a caller asks for them (`arrays_to_dict`)."""
         if self.faiss_index is None:
             raise RuntimeError("index() must be called before retrieve_arrays()")
         return self.faiss_index.search_device(query_emb, top_k, **kwargs)
 
-    def arrays_to_dict(self, scores, ids, query_ids: Sequence[str]) -> dict:
-        s, i = scores.cpu().numpy(), ids.cpu().numpy()
+    def _doc_name(self, pos: int):
         pid = self.faiss_index._passage_ids
-        out = {}
-        for r, qid in enumerate(query_ids):
-            row = {}
-            for doc, sc in zip(i[r].tolist(), s[r].tolist()):
-                if doc < 0:
-                    continue
-                doc = int(pid[doc - self.faiss_index.id_offset]) if pid is not None else doc
-                row[self.rev_mapping[doc] if self.rev_mapping else str(doc)] = float(sc)
-            out[qid] = row
-        return out
+        doc = int(pid[pos - self.faiss_index.id_offset]) if pid is not None else pos
+        return self.rev_mapping[doc] if self.rev_mapping else str(doc)
+
+    def arrays_to_dict(self, scores, ids, query_ids: Sequence[str]) -> dict:
+        return rows_to_dict(scores, ids, query_ids, self._doc_name)
+
+    def retrieve_with_emb(self, query_emb, query_ids: Sequence[str], top_k: int, **kwargs) -> dict:
+        """faiss_search.py:143-173: ``dict[qid -> dict[pid -> score]]`` (the (-inf, -1) padding of a corpus with fewer
+        than k documents is dropped)."""
+        if self.faiss_index is None:
+            raise RuntimeError("index() must be called before retrieve_with_emb()")
+        return self.arrays_to_dict(*self.retrieve_arrays(query_emb, top_k, **kwargs), query_ids)
 
     def save(self, output_dir: str, prefix: str = "my-index", ext: str = "flat"):
+        """The reference's two files (faiss_search.py:113-123): `<prefix>.<ext>.tsv` id map + `<prefix>.<ext>.faiss`."""
+        if not isinstance(self.faiss_index, FlatIPIndex):
+            raise NotImplementedError("save() writes one Faiss file: gather the shards or save per rank with FlatIPIndex.save")
         save_dict_to_tsv(self.mapping, os.path.join(output_dir, f"{prefix}.{ext}.tsv"), keys=self.mapping_tsv_keys)
-        self.faiss_index.save(os.path.join(output_dir, f"{prefix}.{ext}.lrb200"))
+        self.faiss_index.save(os.path.join(output_dir, f"{prefix}.{ext}.faiss"))
 
     def load(self, input_dir: str, prefix: str = "my-index", ext: str = "flat"):
+        """faiss_search.py:99-111, 478-488: reads an index saved by this class or by the reference's FlatIPFaissSearch."""
         self.mapping = load_tsv_to_dict(os.path.join(input_dir, f"{prefix}.{ext}.tsv"), header=True)
         self.rev_mapping = {v: k for k, v in self.mapping.items()}
-        self.faiss_index = FlatIPIndex.load(os.path.join(input_dir, f"{prefix}.{ext}.lrb200"), device=self.device)
-        self.dim_size = self.faiss_index.dim
+        passage_ids = sorted(self.rev_mapping)
+        path = os.path.join(input_dir, f"{prefix}.{ext}.faiss")
+        idx = FlatIPIndex.load(path, passage_ids or None, device=self.device)
+        self.faiss_index = idx.to_gpu(self.group) if self._world() > 1 else idx
+        self.dim_size = idx.dim
+
+    def search_arrays(self, corpus_chunks, query_embeddings, top_k: int, self_pos: Optional[torch.Tensor] = None):
+        """Exact top-k over a corpus that arrives in chunks: every chunk is indexed with its global row offset, searched,
+        and folded into a running device top-k with ``lr_topk_merge``; nothing crosses to the host.  `corpus_chunks`
+        yields ``(first_row, embeddings [n, d])``.  Returns (scores, ids) with ids = global rows."""
+        run = None
+        for first_row, emb in corpus_chunks:
+            idx = self._build_index(emb, None, id_base=first_row)
+            keys = idx.search_keys(query_embeddings, top_k)
+            idx.reset()
+            if self_pos is not None:
+                keys = drop_identical(keys, self_pos)
+            run = keys if run is None else merge_keys([run, keys], top_k)
+        if run is None:
+            raise ValueError("empty corpus")
+        return decode_keys(run)
 
     def search(self, corpus, queries, top_k: int = 1000, score_function: str = None, return_sorted: bool = False,
                ignore_identical_ids: bool = False, **kwargs) -> dict:
-        """Chunked encode -> index -> retrieve -> merge, as DenseRetrievalFaissSearch.search (faiss_search.py:176-293)."""
+        """Chunked encode -> index -> retrieve -> merge of DenseRetrievalFaissSearch.search (faiss_search.py:176-293).
+        The per-chunk results are merged on device; the result dicts are built once at the end."""
         if not isinstance(queries, dict) or not isinstance(corpus, dict):
             raise NotImplementedError("FlatIPSearch.search takes dict corpora / queries")
         query_ids = list(queries.keys())
-        queries_list = [queries[qid] for qid in queries]
-        query_embeddings = self.model.encode_queries(queries_list, batch_size=self.batch_size,
+        query_embeddings = self.model.encode_queries([queries[qid] for qid in queries], batch_size=self.batch_size,
                                                      show_progress_bar=self.show_progress_bar,
                                                      convert_to_tensor=self.convert_to_tensor)
-        corpus_ids = sorted(corpus, key=lambda k_: len(corpus[k_].get("text", "")) if isinstance(corpus[k_], dict)
-                            else len(corpus[k_]), reverse=True)
-        corpus_list = [corpus[cid] for cid in corpus_ids]
-        heaps: dict[str, list] = {qid: [] for qid in query_ids}
-        for start in range(0, len(corpus_list), self.corpus_chunk_size):
-            end = min(start + self.corpus_chunk_size, len(corpus_list))
-            sub = self.model.encode_corpus(corpus_list[start:end], batch_size=self.batch_size,
-                                           show_progress_bar=self.show_progress_bar,
-                                           convert_to_tensor=self.convert_to_tensor)
-            if isinstance(sub, dict):
-                if "dense_reps" not in sub:
-                    raise ValueError(f"HybridModel: Return Multi-vector with keys {sub.keys()}, but not `dense_reps`")
-                sub = sub["dense_reps"]
-            self.index(sub, corpus_ids[start:end])
-            sub_results = self.retrieve_with_emb(query_embeddings, query_ids, top_k=top_k)
-            self._clear()
-            add_to_heap(sub_results, heaps, top_k, ignore_identical_ids)
-        return {qid: {pid: score for score, pid in heaps[qid]} for qid in heaps}
+        corpus_ids, corpus_list = sorted_corpus(corpus)
+
+        def chunks():
+            for start in range(0, len(corpus_list), self.corpus_chunk_size):
+                sub = self.model.encode_corpus(corpus_list[start:start + self.corpus_chunk_size],
+                                               batch_size=self.batch_size, show_progress_bar=self.show_progress_bar,
+                                               convert_to_tensor=self.convert_to_tensor)
+                if isinstance(sub, dict):
+                    if "dense_reps" not in sub:
+                        raise ValueError(f"HybridModel: Return Multi-vector with keys {sub.keys()}, but not `dense_reps`")
+                    sub = sub["dense_reps"]
+                yield start, sub
+
+        scores, ids = self.search_arrays(chunks(), query_embeddings, top_k,
+                                         identical_positions(query_ids, corpus_ids) if ignore_identical_ids else None)
+        return rows_to_dict(scores, ids, query_ids, corpus_ids)
 
 
-def add_to_heap(sub_results: dict, result_heaps: dict, top_k: int, ignore_identical_ids: bool) -> dict:
-    """Host merge with the reference's semantics (hybrid_search.py:182-205) for dict-shaped per-chunk results."""
-    for qid, pid_to_score in sub_results.items():
-        heap = result_heaps.setdefault(qid, [])
-        for pid, score in pid_to_score.items():
-            if ignore_identical_ids and qid == pid:
-                continue
-            if len(heap) < top_k:
-                heapq.heappush(heap, (score, pid))
-            else:
-                heapq.heappushpop(heap, (score, pid))
-    return result_heaps
+def identical_positions(query_ids: Sequence, corpus_ids: Sequence) -> torch.Tensor:
+    """Corpus position of the document that carries the same id as each query (-1 = none), for `ignore_identical_ids`."""
+    pos = {cid: i for i, cid in enumerate(corpus_ids)}
+    return torch.tensor([pos.get(qid, -1) for qid in query_ids], dtype=torch.int64)

@@ -38,37 +38,71 @@ def exchange_candidates(local_keys: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class ShardedFlatIPIndex:
-    """One shard per rank; ``search_device`` returns the exact global top-k on every rank."""
+    """One shard per rank; ``search_device`` returns the exact global top-k on every rank.  Same search surface as
+    ``FlatIPIndex`` (``search_device / search_keys / search / reset``), so the searchers use either."""
 
-    def __init__(self, dim: int, n_total: int, device: Optional[torch.device] = None, group=None):
+    def __init__(self, dim: int, n_total: int, device: Optional[torch.device] = None, group=None, id_base: int = 0):
         from .search import FlatIPIndex  # requires the CUDA library
 
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = int(n_total)
+        self.dim = dim
+        self.id_offset = int(id_base)  # id of global row 0 (a chunk of a larger corpus starts at its first row)
         self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
-        if self.n_total >= (1 << 32) - 2:
+        if self.id_offset + self.n_total >= (1 << 32) - 2:
             raise ValueError("global ids must stay below 2^32")
-        self.local = FlatIPIndex(dim, device=device, id_offset=self.lo)
+        self.local = FlatIPIndex(dim, device=device, id_offset=self.id_offset + self.lo)
+        self.local.reserve(self.hi - self.lo)
+        self._passage_ids = None
+
+    @property
+    def ntotal(self) -> int:
+        return self.n_total
 
     def add_local(self, emb) -> None:
         """Append rows of this rank's shard (global row ids lo .. hi-1, in order)."""
-        self.local.add(emb)
-        if self.local.ntotal > self.hi - self.lo:
+        if self.local.ntotal + emb.shape[0] > self.hi - self.lo:
             raise ValueError("more rows than this rank's shard holds")
+        if emb.shape[0]:
+            self.local.add(emb)
 
-    def search_device(self, query: torch.Tensor, k: int, d_used: Optional[int] = None):
-        from .search import flatip_topk, topk_merge
+    def search_keys(self, query, k: int, d_used: Optional[int] = None) -> torch.Tensor:
+        from .search import topk_merge
 
-        q = query.to(device=self.local.device, dtype=torch.bfloat16)
         if self.local.ntotal != self.hi - self.lo:
             raise RuntimeError(f"shard incomplete: {self.local.ntotal} of {self.hi - self.lo} rows")
+        if self.hi == self.lo:  # more ranks than rows: this rank contributes empty lists
+            q_rows = query.shape[0]
+            keys = torch.zeros((q_rows, k), dtype=torch.int64, device=self.local.device)
+        else:
+            keys = self.local.search_keys(query, k, d_used=d_used)
         if self.world == 1:
-            return flatip_topk(q, self.local.corpus, k, d_used=d_used, id_offset=self.lo)
-        _, _, keys = flatip_topk(q, self.local.corpus, k, d_used=d_used, id_offset=self.lo, return_keys=True)
+            return keys
         gathered = exchange_candidates(keys, self.group)  # [world, Q, k]
-        return topk_merge(gathered, k)
+        return topk_merge(gathered, k, return_keys=True)[2]
+
+    def search_device(self, query, k: int, d_used: Optional[int] = None, return_keys: bool = False):
+        from .search import decode_keys
+
+        keys = self.search_keys(query, k, d_used=d_used)
+        s, i = decode_keys(keys)
+        return (s, i, keys) if return_keys else (s, i)
+
+    def search(self, query_embeddings, k: int, **kwargs):
+        """FaissIndex.search arrays (faiss_index.py:27-40) of the global result, identical on every rank."""
+        import numpy as np
+
+        s, i = self.search_device(query_embeddings, k)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        if self._passage_ids is not None:
+            valid = i >= 0
+            i = np.where(valid, self._passage_ids[np.where(valid, i - self.id_offset, 0)], -1)
+        return s, i
+
+    def reset(self) -> None:
+        self.local.reset()
 
 
 class ShardedImpactIndex:

@@ -21,6 +21,7 @@ from . import _C
 from ._util import Workspace, require_cuda, stream_ptr
 
 _WS = Workspace()
+MAX_TOP_K = 1024  # lr_sparse_score_topk's list capacity
 
 
 def json_to_csr(corpus_emb: Sequence[dict]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -254,8 +255,12 @@ class ImpactSearch:
     def retrieve_arrays(self, query_emb: Sequence, top_k: int):
         """Device arrays (scores f32 [Q,k], doc positions i64 [Q,k], -1 padded) — no dict materialisation."""
         idx = self._ensure_index()
+        if int(top_k) > MAX_TOP_K:
+            # the reference hands `-hits top_k` to Anserini unchanged (anserini_search.py:178-202); silently returning
+            # fewer sparse hits would change the min-max normalisation of a hybrid fusion
+            raise ValueError(f"top_k={top_k} exceeds the sparse kernel's limit of {MAX_TOP_K} results per query")
         qi, qt, qc = parse_queries(query_emb, idx.V)
-        return idx.search_device(qi, qt, qc, min(int(top_k), 1024))
+        return idx.search_device(qi, qt, qc, int(top_k))
 
     def _ensure_index(self) -> ImpactIndex:
         if self._index is None:
@@ -271,19 +276,42 @@ class ImpactSearch:
         return self._index
 
     def retrieve_with_emb(self, query_emb: Sequence, query_ids: Sequence[str], top_k: int) -> dict:
-        idx = self._ensure_index()
-        qi, qt, qc = parse_queries(query_emb, idx.V)
-        k = min(int(top_k), 1024)
-        scores, ids = idx.search_device(qi, qt, qc, k)
-        scores = scores.cpu().numpy()
-        ids = ids.cpu().numpy()
-        results: dict[str, dict[str, float]] = {}
-        for i, qid in enumerate(query_ids):
-            row = {}
-            for doc, s in zip(ids[i].tolist(), scores[i].tolist()):
-                if doc < 0:
-                    continue
-                row[self._corpus_ids[doc]] = float(s)
-            if row:  # Lucene writes no TREC line for a query without hits (anserini_search.py:208-214)
-                results[qid] = row
+        """anserini_search.py:143-216: ``dict[qid -> dict[pid -> score]]``; Lucene writes no TREC line for a query without
+        hits (:208-214), so such queries are absent."""
+        from .search import rows_to_dict
+
+        scores, ids = self.retrieve_arrays(query_emb, top_k)
+        return rows_to_dict(scores, ids, query_ids, self._corpus_ids, keep_empty=False)
+
+    def search(self, corpus, queries, top_k: int = 1000, score_function: str = None, return_sorted: bool = False,
+               ignore_identical_ids: bool = False, **kwargs) -> dict:
+        """AnseriniSearch.search (anserini_search.py:218-309): encode the queries, encode + index the corpus in chunks
+        (longest document first), retrieve once, clear.  Like the reference, `ignore_identical_ids` is accepted and unused."""
+        from .search import sorted_corpus
+
+        if not isinstance(queries, dict) or not isinstance(corpus, dict):
+            raise NotImplementedError("ImpactSearch.search takes dict corpora / queries")
+        query_ids = list(queries.keys())
+        query_embeddings = self.model.encode_queries([queries[qid] for qid in queries], batch_size=self.batch_size,
+                                                     show_progress_bar=self.show_progress_bar,
+                                                     convert_to_tensor=self.convert_to_tensor)
+        if isinstance(query_embeddings, dict):
+            for key in ("token_id_reps", "sparse_reps"):
+                if query_embeddings.get(key) is not None:
+                    query_embeddings = query_embeddings[key]
+                    break
+            else:
+                raise ValueError(f"HybridModel: query embeddings with keys {query_embeddings.keys()} hold no sparse vector")
+        corpus_ids, corpus_list = sorted_corpus(corpus)
+        for start in range(0, len(corpus_list), self.corpus_chunk_size):
+            sub = self.model.encode_corpus(corpus_list[start:start + self.corpus_chunk_size], batch_size=self.batch_size,
+                                           show_progress_bar=self.show_progress_bar,
+                                           convert_to_tensor=self.convert_to_tensor)
+            if isinstance(sub, dict):
+                if "sparse_reps" not in sub:
+                    raise ValueError(f"HybridModel: Return Multi-vector with keys {sub.keys()}, but not `sparse_reps`")
+                sub = sub["sparse_reps"]
+            self.index(sub, corpus_ids[start:start + self.corpus_chunk_size])
+        results = self.retrieve_with_emb(query_embeddings, query_ids, top_k=top_k)
+        self._clear()
         return results

@@ -188,6 +188,7 @@ def test_flatip_two_phase_warm_start_is_exact(monkeypatch, prefix_docs, cluster)
     including ties that straddle the prefix boundary and results that live entirely inside the prefix."""
     monkeypatch.setenv("LR_FLATIP_PREFIX_DOCS", str(prefix_docs))
     monkeypatch.setenv("LR_FLATIP_CLUSTER", str(cluster))
+    lr._C.reload_env()  # the knobs are cached after the first call
     gen = torch.Generator().manual_seed(prefix_docs)
     Q, N, d, k = 300, 30000, 128, 100
     q = F.normalize(torch.randn(Q, d, generator=gen), dim=-1).bfloat16()
@@ -207,6 +208,8 @@ def test_flatip_two_phase_warm_start_is_exact(monkeypatch, prefix_docs, cluster)
     s2, i2 = lr.flatip_topk(qq.bfloat16().cuda(), base.bfloat16().cuda(), 50)
     _, ei2 = oracle.flatip_topk(qq.bfloat16().float(), base.bfloat16().float(), 50)
     np.testing.assert_array_equal(_np(i2), ei2)
+    monkeypatch.undo()
+    lr._C.reload_env()
 
 
 def test_searcher_surface_matches_reference_protocol():
@@ -222,12 +225,15 @@ def test_searcher_surface_matches_reference_protocol():
     for r, qid in enumerate(qids):
         assert list(res[qid].keys()) == [cids[j] for j in ei[r]]
         np.testing.assert_allclose(list(res[qid].values()), es[r], rtol=1e-2, atol=1e-4)
-    # chunked search + heap merge == one-shot search (hybrid_search.py:301-344)
+    # chunked search + merge == one-shot search (hybrid_search.py:301-344); the merge runs on device (lr_topk_merge)
+    s_c, i_c = search.search_arrays(((lo, corpus[lo:lo + 250]) for lo in range(0, 600, 250)), queries, 10)
+    np.testing.assert_array_equal(_np(i_c), ei)
+    # ... and equals the reference's host heap merge of the per-chunk dicts (played by the oracle)
     heaps = {}
     for lo in range(0, 600, 250):
         search._clear()
         search.index(corpus[lo:lo + 250], cids[lo:lo + 250])
-        lr.search.add_to_heap(search.retrieve_with_emb(queries, qids, 10), heaps, 10, False)
+        oracle.add_to_heap(search.retrieve_with_emb(queries, qids, 10), heaps, 10, False)
     for r, qid in enumerate(qids):
         assert sorted(p for _, p in heaps[qid]) == sorted(res[qid].keys())
     search._clear()
@@ -669,6 +675,167 @@ def test_short_rows_at_scale_refresh_passes_and_two_epilogue_sets():
     out = (ctypes.c_int64 * 16)()
     C.load().lr_flatip_plan(Q, N, k, out)
     assert out[1] == 1 and out[5] == 128  # pairs + the 32768-document prefix: the regime this test is about
+
+
+def _plan_of(Q, N, k, d):
+    import ctypes
+    from lightretriever_b200 import _C as C
+    out, rows, flags = (ctypes.c_int64 * 16)(), (ctypes.c_int64 * 64)(), (ctypes.c_int64 * 2)()
+    C.load().lr_flatip_plan(Q, N, k, out)
+    n = C.load().lr_flatip_plan_passes(Q, N, k, d, rows, 16, flags)
+    return list(out), [tuple(rows[4 * i:4 * i + 4]) for i in range(n)]
+
+
+@pytest.mark.parametrize("k", [100, 1000])
+def test_headline_regime_pairs_team_schedule_prefix_full_width(k):
+    """The regime that carries the headline number (bench.py: 10k queries x 8.8M x 4096): cta_group::2 pairs on the team
+    schedule, one-tile progress window, warm-start prefix, full-width rows (64 k-blocks per tile) — at the smallest size
+    that selects exactly that plan (asserted).  Two corpora: random, and rows SORTED by similarity to query 0 (every later
+    document beats that query's running threshold: the worst case for warm-start pruning and list cuts).  Properties on
+    every row (planted document first, order, unique ids, fp32 recomputation of the returned scores) and full parity
+    against an fp32 matmul of the same bf16 values on 48 sampled rows incl. the adversarial one."""
+    torch.manual_seed(17)
+    Q, N, d = 2304, 1_100_000, 4096
+    plan, passes = _plan_of(Q, N, k, d)
+    assert plan[0] == 2 and plan[1] == 1, plan            # cluster of two, cta_group::2 pair
+    assert len(passes) == 2 and passes[0][0] == 0 and passes[-1][3] == 1, passes   # prefix, then main on the team schedule
+    assert passes[0][1] == (128 if k == 100 else 268), passes
+    c = torch.empty((N, d), dtype=torch.bfloat16, device="cuda")
+    for lo in range(0, N, 1 << 17):
+        c[lo:lo + (1 << 17)] = F.normalize(torch.randn(min(1 << 17, N - lo), d, device="cuda"), dim=-1).bfloat16()
+    q = F.normalize(torch.randn(Q, d, device="cuda"), dim=-1).bfloat16()
+    planted = torch.randperm(N, device="cuda")[:Q]
+    c[planted] = q
+    sample = torch.cat([torch.tensor([0, 1, 127, 128, 255, 256, Q - 1], device="cuda"),
+                        torch.randperm(Q, device="cuda")[:41]]).unique()
+
+    def check(corpus, planted_at):
+        s, i = lr.flatip_topk(q, corpus, k)
+        assert bool((i[:, 0] == planted_at).all())
+        assert bool((s[:, :-1] >= s[:, 1:]).all())
+        assert bool((i.sort(dim=1).values.diff(dim=1) > 0).all())          # unique ids in every row
+        for lo in range(0, Q, 256):                                        # returned scores == fp32 recomputation
+            rec = torch.einsum("qd,qkd->qk", q[lo:lo + 256].float(), corpus[i[lo:lo + 256]].float())
+            torch.testing.assert_close(s[lo:lo + 256], rec, rtol=1e-2, atol=1e-4)
+        ref = torch.cat([q[sample].float() @ corpus[lo:lo + (1 << 18)].float().T for lo in range(0, N, 1 << 18)], dim=1)
+        oracle.check_topk_parity(_np(s[sample]), _np(i[sample]), ref.cpu().numpy(), k, rtol=1e-2)
+
+    check(c, planted)
+    # adversarial order for query 0: ascending similarity (its planted twin ends up last)
+    sim = torch.cat([c[lo:lo + (1 << 18)].float() @ q[0].float() for lo in range(0, N, 1 << 18)])
+    order = torch.argsort(sim)
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(N, device="cuda")
+    c2 = c[order]
+    del c
+    check(c2, inv[planted])
+
+
+def test_faiss_flat_file_roundtrip_and_sharded_load(tmp_path):
+    """Row f3: FlatIPSearch.save writes the reference's two files (<prefix>.flat.tsv + <prefix>.flat.faiss, an IndexFlatIP
+    in Faiss's on-disk layout); load reads them straight into HBM — whole, or a row range (a rank's shard)."""
+    gen = torch.Generator().manual_seed(8)
+    corpus = F.normalize(torch.randn(700, 64, generator=gen), dim=-1).bfloat16().float()  # bf16-exact: fp32 file is lossless
+    queries = F.normalize(torch.randn(4, 64, generator=gen), dim=-1)
+    cids = [f"doc-{j}" for j in range(700)]
+    qids = [f"q{j}" for j in range(4)]
+    a = lr.FlatIPSearch(model=None)
+    a.index(corpus, cids)
+    want = a.retrieve_with_emb(queries, qids, 15)
+    a.save(str(tmp_path), prefix="idx")
+    assert (tmp_path / "idx.flat.faiss").stat().st_size == 45 + 700 * 64 * 4
+    b = lr.FlatIPSearch(model=None)
+    b.load(str(tmp_path), prefix="idx")
+    assert b.retrieve_with_emb(queries, qids, 15) == want
+    shard = lr.FlatIPIndex.load(str(tmp_path / "idx.flat.faiss"), rows=(300, 700), id_offset=300)
+    s, i = shard.search_device(queries, 15)
+    es, ei = oracle.flatip_topk(queries.bfloat16().float(), corpus[300:], 15, id_offset=300)
+    np.testing.assert_array_equal(_np(i), ei)
+
+
+def test_fusion_dict_adapters_match_reference_golden(golden_dir):
+    """fuse_scores_linear / fuse_scores_rrf (dict in, dict out) are adapters over lr_fuse_topk: against the outputs of the
+    reference's own functions (tests/golden/fusion.json, float64)."""
+    g = json.load(open(os.path.join(golden_dir, "fusion.json")))
+    lin = lr.fuse_scores_linear([g["dense"], g["sparse"]], weights=[0.7, 0.3])
+    rrf = lr.fuse_scores_rrf([g["dense"], g["sparse"]])
+    assert lin.keys() == g["linear"].keys() and rrf.keys() == g["rrf"].keys()
+    for q in g["linear"]:
+        assert lin[q].keys() == g["linear"][q].keys() and rrf[q].keys() == g["rrf"][q].keys()
+        for p, v in g["linear"][q].items():
+            assert abs(lin[q][p] - v) < 1e-12
+        for p, v in g["rrf"][q].items():
+            assert abs(rrf[q][p] - v) < 1e-12
+
+
+def test_hybrid_search_chunk_loop_runs_without_host_heaps(monkeypatch):
+    """HybridSearch.search over a 3-chunk corpus with two dense query kinds, ignore_identical_ids and rrf: per-chunk results
+    are merged by lr_topk_merge and fused by lr_fuse_topk — no heapq call — and equal the reference flow played by the
+    oracle (per-chunk top-k dicts -> _add_to_heap -> fuse)."""
+    import heapq
+
+    def boom(*a, **kw):
+        raise AssertionError("host heap merge on the search path")
+
+    gen = torch.Generator().manual_seed(31)
+    n_docs, n_q, d, V, k = 330, 5, 64, 83, 12
+    doc_vec = F.normalize(torch.randn(n_docs, d, generator=gen), dim=-1)
+    q_den = F.normalize(torch.randn(n_q, d, generator=gen), dim=-1)
+    q_emb = F.normalize(torch.randn(n_q, d, generator=gen), dim=-1)
+    rng = np.random.default_rng(6)
+    doc_sparse = [{str(int(t)): int(rng.integers(1, 300)) for t in rng.choice(V, 10, replace=False)} for _ in range(n_docs)]
+    q_tok = [" ".join(str(int(t)) for t in rng.integers(0, V, size=5)) for _ in range(n_q)]
+    corpus = {f"d{j}": {"text": "x" * (1 + (j * 7) % 11), "j": j} for j in range(n_docs)}
+    queries = {(f"d{j * 3}" if j < 3 else f"q{j}"): f"query {j}" for j in range(n_q)}   # three queries ARE corpus documents
+    doc_vec[0], doc_vec[3], doc_vec[6] = q_emb[0], q_emb[1], q_emb[2]                   # ... and would retrieve themselves
+
+    class FakeModel:
+        def encode_queries(self, queries, **kw):
+            return {"dense_reps": q_den, "emb_reps": q_emb, "token_id_reps": q_tok}
+
+        def encode_corpus(self, corpus, **kw):
+            idx = [c["j"] for c in corpus]
+            return {"dense_reps": doc_vec[idx], "sparse_reps": [doc_sparse[j] for j in idx]}
+
+    hs = lr.HybridSearch(FakeModel(), batch_size=16, corpus_chunk_size=128, return_all_results=True, vocab_size=V,
+                         score_fuse_method="rrf")
+    with monkeypatch.context() as m:
+        m.setattr(heapq, "heappush", boom)
+        m.setattr(heapq, "heappushpop", boom)
+        res = hs.search(corpus, queries, top_k=k, ignore_identical_ids=True)
+    # reference flow on the oracle
+    cids = sorted(corpus, key=lambda c_: len(corpus[c_]["text"]), reverse=True)
+    order = [corpus[c_]["j"] for c_ in cids]
+    qids = list(queries)
+    cb = doc_vec.bfloat16().float()[order]
+    for name, qv in (("den", q_den), ("emb", q_emb)):
+        heaps = {qid: [] for qid in qids}
+        for lo in range(0, n_docs, 128):
+            es, ei = oracle.flatip_topk(qv.bfloat16().float(), cb[lo:lo + 128], k, id_offset=lo)
+            sub = {qid: {cids[j]: float(s_) for s_, j in zip(es[r], ei[r])} for r, qid in enumerate(qids)}
+            oracle.add_to_heap(sub, heaps, k, True)
+        want = {qid: {pid: sc for sc, pid in heaps[qid]} for qid in qids}
+        assert res[name].keys() == want.keys()
+        for qid in qids:
+            assert res[name][qid].keys() == want[qid].keys(), (name, qid)
+            assert qid not in res[name][qid]
+            np.testing.assert_allclose([res[name][qid][p] for p in want[qid]], list(want[qid].values()), rtol=1e-2, atol=1e-4)
+    ts, ti = oracle.impact_topk([oracle.query_counts([int(t) for t in s_.split()]) for s_ in q_tok],
+                                [{int(a): b for a, b in doc_sparse[j].items()} for j in order], k)
+    tok = {qid: {cids[j]: float(s_) for s_, j in zip(ts[r], ti[r]) if j >= 0} for r, qid in enumerate(qids)}
+    assert res["tok"] == {q_: v for q_, v in tok.items() if v}
+    fused = oracle.fuse_rrf([res["emb"], res["tok"]])
+    assert res["emb_tok"].keys() == fused.keys()
+    for qid in fused:
+        assert res["emb_tok"][qid].keys() == fused[qid].keys()
+        for pid, v in fused[qid].items():
+            assert abs(res["emb_tok"][qid][pid] - v) < 1e-12
+    # the sparse searcher's own search() (anserini_search.py:218-309)
+    sp = lr.ImpactSearch(FakeModel(), batch_size=16, corpus_chunk_size=100, vocab_size=V)
+    assert sp.search(corpus, queries, top_k=k) == res["tok"]
+    with pytest.raises(ValueError):
+        sp.index(doc_sparse[:4], ["a", "b", "c", "d"])
+        sp.retrieve_with_emb(q_tok, qids, 2000)   # beyond the sparse kernel's limit: an error, not a silent clamp
 
 
 def test_online_searcher_graph_replay_matches_eager():

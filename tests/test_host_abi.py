@@ -134,20 +134,44 @@ def test_sparse_mask_matches_reference(golden_dir):
     np.testing.assert_array_equal(lr.get_sparse_attention_mask(ids, am, 7, True).numpy(), g["mask_rp"])
 
 
-def test_fusion_matches_reference(golden_dir):
+def test_fusion_dict_packing_for_the_device_kernel(golden_dir):
+    """The dict-shaped fusion functions are adapters over lr_fuse_topk: this is their host half (dicts -> sorted arrays
+    over a joint id numbering); the arithmetic is checked against the same golden on the GPU (test_gpu_parity)."""
+    from lightretriever_b200.hybrid import _pack_systems
     g = json.load(open(os.path.join(golden_dir, "fusion.json")))
-    lin = lr.fuse_scores_linear([g["dense"], g["sparse"]], weights=[0.7, 0.3])
-    rrf = lr.fuse_scores_rrf([g["dense"], g["sparse"]])
-    for q in g["linear"]:
-        for p, v in g["linear"][q].items():
-            assert abs(lin[q][p] - v) < 1e-12
-        for p, v in g["rrf"][q].items():
-            assert abs(rrf[q][p] - v) < 1e-12
-    from lightretriever_b200.search import add_to_heap
-    heaps = {}
-    for ch in g["chunks"]:
-        add_to_heap(ch, heaps, 7, False)
-    assert {q: sorted([s, p] for s, p in v) for q, v in heaps.items()} == g["heap_top7"]
+    qn, pn, ((s0, i0), (s1, i1)) = _pack_systems([g["dense"], g["sparse"]], "cpu")
+    assert sorted(qn) == sorted(set(g["dense"]) | set(g["sparse"]))
+    for res, s, i in ((g["dense"], s0, i0), (g["sparse"], s1, i1)):
+        assert s.dtype == torch.float64 and i.dtype == torch.int64
+        for r, q in enumerate(qn):
+            row = res.get(q, {})
+            n = len(row)
+            assert (i[r, n:] == -1).all() and (i[r, :n] >= 0).all()
+            assert {pn[j]: float(v) for j, v in zip(i[r, :n].tolist(), s[r, :n].tolist())} == {k: float(v) for k, v in row.items()}
+            assert bool((s[r, :max(n - 1, 0)] >= s[r, 1:n]).all())  # rank = position (rrf)
+    with pytest.raises(NotImplementedError):
+        _pack_systems([{}, {}, {}], "cpu")
+
+
+def test_faiss_flat_file_layout(tmp_path):
+    """The on-disk IndexFlatIP layout FlatIPIndex.save/load speak (faiss_index.py:42-43, faiss_search.py:478-488): fourcc
+    "IxFI", d, ntotal, two dummies, is_trained, metric 0, float count, fp32 rows.  Header checked byte for byte against a
+    file assembled by hand here (Faiss itself is absent: format restated from index_write.cpp, parity unpinned)."""
+    import struct
+    from lightretriever_b200.search import _FAISS_FLAT_IP, _FAISS_HEADER
+    assert _FAISS_HEADER.size == 45 and struct.pack("<I", _FAISS_FLAT_IP) == b"IxFI"
+    rows = np.arange(12, dtype=np.float32).reshape(3, 4)
+    blob = (b"IxFI" + struct.pack("<i", 4) + struct.pack("<q", 3) + struct.pack("<qq", 1 << 20, 1 << 20) + b"\x01" +
+            struct.pack("<i", 0) + struct.pack("<Q", 12) + rows.tobytes())
+    assert _FAISS_HEADER.unpack(blob[:45]) == (_FAISS_FLAT_IP, 4, 3, 1 << 20, 1 << 20, True, 0, 12)
+    path = tmp_path / "x.flat.faiss"
+    path.write_bytes(blob)
+    got = np.memmap(path, dtype=np.float32, mode="r", offset=45, shape=(3, 4))
+    np.testing.assert_array_equal(np.asarray(got), rows)
+    bad = tmp_path / "bad.faiss"
+    bad.write_bytes(b"IxF2" + blob[4:])
+    with pytest.raises((ValueError, RuntimeError)):
+        lr.FlatIPIndex.load(str(bad))
 
 
 def test_shard_ranges_partition_the_corpus():
