@@ -112,6 +112,27 @@ int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
                    float* out_scores, int64_t* out_ids, uint64_t* out_keys,
                    void* workspace, size_t ws_bytes, void* stream);
 
+/* Row-sharded search, one shard per GPU (Faiss GpuMultipleClonerOptions.shard = True, retriever/faiss_index.py:60-70):
+ * the warm start is shared between the shards.  lr_flatip_topk_begin scores this shard's 1/n_shards share of the
+ * warm-start prefix and writes its top-k there as sorted keys out_prefix_keys [Q, k] (local ids; zeros when the plan of
+ * this shape has no warm-start pass).  The caller exchanges them (NCCL all-gather), merges them per query with
+ * lr_topk_merge and hands the merged [Q, k] keys to lr_flatip_topk_finish as seed_keys: the k-th best score of the whole
+ * prefix is a lower bound of the global k-th score, so every shard runs its remaining passes with the thresholds of the
+ * unsharded search at 1/n_shards of its warm-start cost.  The per-shard result then holds only documents that can
+ * still reach the GLOBAL top-k: it may have fewer than k entries (tail (-inf, -1), key 0).  seed_keys NULL = no exchange.
+ * Both calls take the same arguments, workspace (>= lr_flatip_workspace_bytes_sharded) and stream; the workspace
+ * carries the state from one to the other and must not be used in between. */
+size_t lr_flatip_workspace_bytes_sharded(int64_t Q, int64_t N, int k, int64_t d_used, int n_shards);
+int lr_flatip_topk_begin(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
+                         int64_t Q, int64_t N, int64_t d_used, const float* q_scale, const float* c_scale,
+                         int k, int n_shards, uint64_t* out_prefix_keys /*[Q,k]*/,
+                         void* workspace, size_t ws_bytes, void* stream);
+int lr_flatip_topk_finish(const void* q, int64_t ldq, const void* corpus, int64_t ldc,
+                          int64_t Q, int64_t N, int64_t d_used, const float* q_scale, const float* c_scale,
+                          int64_t id_offset, int k, int n_shards, const uint64_t* seed_keys /*[Q,k] or NULL*/,
+                          float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                          void* workspace, size_t ws_bytes, void* stream);
+
 /* Debug / parity helper: the same TMA+tcgen05 main loop with a plain store
  * epilogue, scores [Q, N] f32 (small shapes only). Definition of the score:
  * torch.matmul(q, p.T)  finetune/modeling_encoder.py:414-427. */
@@ -135,6 +156,9 @@ int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16);
  * out_flags[1] = candidate lists per split. */
 int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used, int64_t* out_rows, int max_passes,
                           int64_t* out_flags2);
+/* Same for one shard of a row-sharded search (lr_flatip_topk_begin / _finish): the warm-start prefix is 1/n_shards long. */
+int lr_flatip_plan_passes_sharded(int64_t Q, int64_t N, int k, int64_t d_used, int n_shards, int64_t* out_rows,
+                                  int max_passes, int64_t* out_flags2);
 
 /* Plan of the last lr_flatip_topk call on this thread (for bench / DESIGN):
  * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=rounds */

@@ -29,6 +29,11 @@ PROTOTYPES = {
     "lr_flatip_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "lr_flatip_workspace_bytes_for": (_sz, [_i64, _i64, _i32, _i64]),
     "lr_flatip_topk": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lr_flatip_workspace_bytes_sharded": (_sz, [_i64, _i64, _i32, _i64, _i32]),
+    "lr_flatip_topk_begin": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "lr_flatip_topk_finish": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp,
+                                     _vp, _sz, _vp]),
+    "lr_flatip_plan_passes_sharded": (_i32, [_i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp]),
     "lr_flatip_scores": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "lr_flatip_last_plan": (_i32, [_vp]),
     "lr_flatip_plan": (_i32, [_i64, _i64, _i32, _vp]),

@@ -145,7 +145,7 @@ static PassPlan plan_pass(int m_groups, int n_clusters, int tile_begin, int tile
   return pp;
 }
 
-static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used) {
+static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used, int shards) {
   FlatipPlan pl{};
   const FlatipEnv& env = flatip_env();
   // Candidate-list capacity.  The running threshold of a row only rises when its list is cut back to the top-k, so
@@ -182,7 +182,7 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
   // Phase A (warm start) when the search is compute-bound and long enough to amortise it.  Measured on the 1.1M x 4096
   // shard shape (profiles/k2_schedule_sweeps_r1.md): a 32768-document prefix brings the main pass within 2% of a run
   // with perfect thresholds; 4k..8k-document prefixes do not pay for themselves.
-  int prefix_tiles = 0;
+  int prefix_tiles = 0, pt_global = 0;
   int prefix_splits_forced = 0;
   const int want = env.prefix_docs;
   if (want != 0) {
@@ -192,6 +192,15 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
     int pt = int((docs + BN - 1) / BN);
     if (want < 0 && pt > pl.n_tiles / 16) pt = pl.n_tiles / 16;
     const bool big_enough = want > 0 || (pl.m_groups >= 4 && pt >= 128 && pl.n_tiles >= 32 * 128);
+    // Row-sharded search (lr_flatip_topk_begin / _finish): this shard scores 1/shards of the warm-start prefix and the
+    // caller exchanges the per-shard prefix top-k, so every shard starts the main pass with the k-th best score of the
+    // whole prefix — the thresholds of the unsharded search at 1/shards of its warm-start cost per GPU.
+    pt_global = pt;
+    if (shards > 1) {
+      pt = (pt + shards - 1) / shards;
+      const int min_pt = int((2 * int64_t(k) + BN - 1) / BN);
+      if (pt < min_pt) pt = min_pt;
+    }
     if (big_enough && pt < pl.n_tiles) prefix_tiles = pt;
     // Small query batches (online serving, HBM-bound): a prefix of one tile per cluster, every cluster scoring a
     // different tile, costs one tile time and removes the cold-start cuts, which otherwise pile up in the one or two
@@ -213,17 +222,19 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
   int main_begin = prefix_tiles;
   pl.n_mid = 0;
   const int refresh = env.refresh >= 0 ? env.refresh : (d_used <= 1024 ? 1 : 0);
-  if (refresh && prefix_tiles >= 128 && prefix_tiles == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN)) {
+  if (refresh && pt_global >= 128 && prefix_tiles > 0 &&
+      pt_global == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN)) {
     int growth = env.refresh_growth;
     if (growth < 2) growth = 2;
-    int64_t len = int64_t(prefix_tiles) * (growth - 1);
-    while (pl.n_mid < MAX_MID && main_begin + len + len < pl.n_tiles) {
-      pl.mid[pl.n_mid] = plan_pass(pl.m_groups, geo.n_clusters, main_begin, main_begin + int(len), s_cap, 0);
+    // ranges end at growth^i times the WHOLE prefix (a shard's thresholds start from the exchanged k-th best of it)
+    int64_t end = int64_t(pt_global) * growth;
+    while (pl.n_mid < MAX_MID && end + (end - main_begin) < pl.n_tiles) {
+      pl.mid[pl.n_mid] = plan_pass(pl.m_groups, geo.n_clusters, main_begin, int(end), s_cap, 0);
       pl.mid[pl.n_mid].band_size = pl.band_size;
       pl.mid[pl.n_mid].n_bands = pl.n_bands;
       ++pl.n_mid;
-      main_begin += int(len);
-      len *= growth;
+      main_begin = int(end);
+      end *= growth;
     }
   }
   pl.main = plan_pass(pl.m_groups, geo.n_clusters, main_begin, pl.n_tiles, s_cap, env.splits);
@@ -260,10 +271,10 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
 
 // The planner loops (plan_pass: up to 4 x clusters split counts; plan_teams: band widths x multiples) run once per search
 // shape: the online path repeats the same (Q, N, k, d_used) every request.  Per-thread cache, dropped on lr_reload_env().
-static const FlatipPlan& make_plan(int64_t Q, int64_t N, int k, int64_t d_used) {
+static const FlatipPlan& make_plan(int64_t Q, int64_t N, int k, int64_t d_used, int shards = 1) {
   struct Entry {
     int64_t Q, N, d_used;
-    int k, sms;
+    int k, sms, shards;
     FlatipPlan pl;
   };
   constexpr int kEntries = 16;
@@ -277,13 +288,13 @@ static const FlatipPlan& make_plan(int64_t Q, int64_t N, int k, int64_t d_used) 
   const int sms = sm_count();
   for (int i = 0; i < n_cached; ++i) {
     const Entry& e = cache[i];
-    if (e.Q == Q && e.N == N && e.k == k && e.d_used == d_used && e.sms == sms) return e.pl;
+    if (e.Q == Q && e.N == N && e.k == k && e.d_used == d_used && e.sms == sms && e.shards == shards) return e.pl;
   }
   Entry& e = cache[next_slot];
   next_slot = (next_slot + 1) % kEntries;
   if (n_cached < kEntries) ++n_cached;
-  e.Q = Q; e.N = N; e.k = k; e.d_used = d_used; e.sms = sms;
-  e.pl = make_plan_uncached(Q, N, k, d_used);
+  e.Q = Q; e.N = N; e.k = k; e.d_used = d_used; e.sms = sms; e.shards = shards;
+  e.pl = make_plan_uncached(Q, N, k, d_used, shards);
   return e.pl;
 }
 
@@ -352,7 +363,7 @@ static int launch_pass(const FlatipPlan& pl, const PassPlan& pp, const CUtensorM
 // documents have been seen — any k documents give a valid lower bound of the final k-th score).
 __global__ void carry_topk_kernel(const uint64_t* __restrict__ merged, int64_t key_stride, int k, int64_t q_pad,
                                   int64_t Q, uint64_t* __restrict__ dst, uint32_t* __restrict__ gthr,
-                                  int32_t* __restrict__ counts) {
+                                  int32_t* __restrict__ counts, const uint64_t* __restrict__ seed) {
   const int64_t q = blockIdx.x;
   if (q >= q_pad) return;
   if (q < Q)
@@ -362,10 +373,22 @@ __global__ void carry_topk_kernel(const uint64_t* __restrict__ merged, int64_t k
     if (q < Q) {
       const uint64_t kth = merged[q * key_stride + (k - 1)];
       if (kth != 0ull) g = key_hi(kth);
+      if (seed) {  // [Q, k] sorted keys of the union of every shard's prefix: its k-th best bounds the global k-th score
+        const uint64_t sk = seed[q * int64_t(k) + (k - 1)];
+        if (sk != 0ull && key_hi(sk) > g) g = key_hi(sk);
+      }
     }
     gthr[q] = g;
     counts[q] = q < Q ? k : 0;
   }
+}
+
+// gthr[q] = max(gthr[q], score key of seed[q][k-1]) for a sharded search whose local plan has no warm-start pass
+__global__ void seed_thresholds_kernel(const uint64_t* __restrict__ seed, int k, int64_t Q, uint32_t* __restrict__ gthr) {
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const uint64_t sk = seed[q * int64_t(k) + (k - 1)];
+  if (sk != 0ull && key_hi(sk) > gthr[q]) gthr[q] = key_hi(sk);
 }
 
 }  // namespace lr
@@ -399,11 +422,11 @@ extern "C" int lr_flatip_plan(int64_t Q, int64_t N, int k, int64_t* out16) {
   return LR_OK;
 }
 
-extern "C" int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used, int64_t* out_rows, int max_passes,
-                                     int64_t* out_flags2) {
-  LR_CHECK_ARG(out_rows && out_flags2 && max_passes >= 1 && Q >= 1 && N >= 1 && k >= 1 && k <= 2048 && d_used >= 1,
-               "flatip_plan_passes: bad arguments");
-  const FlatipPlan pl = make_plan(Q, N, k, d_used);
+extern "C" int lr_flatip_plan_passes_sharded(int64_t Q, int64_t N, int k, int64_t d_used, int n_shards, int64_t* out_rows,
+                                             int max_passes, int64_t* out_flags2) {
+  LR_CHECK_ARG(out_rows && out_flags2 && max_passes >= 1 && Q >= 1 && N >= 1 && k >= 1 && k <= 2048 && d_used >= 1 &&
+                   n_shards >= 1, "flatip_plan_passes: bad arguments");
+  const FlatipPlan pl = make_plan(Q, N, k, d_used, n_shards);
   int n = 0;
   auto put = [&](const PassPlan& pp) {
     if (n < max_passes) {
@@ -419,6 +442,11 @@ extern "C" int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used
   return n;
 }
 
+extern "C" int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used, int64_t* out_rows, int max_passes,
+                                     int64_t* out_flags2) {
+  return lr_flatip_plan_passes_sharded(Q, N, k, d_used, 1, out_rows, max_passes, out_flags2);
+}
+
 extern "C" int lr_flatip_last_plan(int64_t* out8) {
   const FlatipPlan& pl = g_last_plan;
   out8[0] = pl.m_tiles; out8[1] = pl.n_tiles; out8[2] = pl.main.splits; out8[3] = pl.main.band_size * pl.cl;
@@ -426,16 +454,21 @@ extern "C" int lr_flatip_last_plan(int64_t* out8) {
   return LR_OK;
 }
 
-extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,
-                              int64_t d_used, const float* q_scale, const float* c_scale, int64_t id_offset, int k,
-                              float* out_scores, int64_t* out_ids, uint64_t* out_keys, void* workspace,
-                              size_t ws_bytes, void* stream) {
+// One search = phase A (warm-start prefix -> `carry` + thresholds) then the refresh passes and the main pass.  The
+// unsharded entry point runs both; a row-sharded search runs them as two calls with the caller's exchange of the
+// per-shard prefix top-k in between (RUN_PREFIX writes prefix_keys_out, RUN_REST reads seed_keys).
+enum { RUN_PREFIX = 1, RUN_REST = 2 };
+static int flatip_run(int phases, int shards, const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q,
+                      int64_t N, int64_t d_used, const float* q_scale, const float* c_scale, int64_t id_offset, int k,
+                      uint64_t* prefix_keys_out, const uint64_t* seed_keys, float* out_scores, int64_t* out_ids,
+                      uint64_t* out_keys, void* workspace, size_t ws_bytes, void* stream) {
   int rc = check_flatip_args(q, ldq, corpus, ldc, Q, N, d_used);
   if (rc) return rc;
   LR_CHECK_ARG(k >= 1 && k <= 2048, "flatip: k (%d) must be in [1, 2048]", k);
+  LR_CHECK_ARG(shards >= 1 && shards <= 1024, "flatip: n_shards (%d) must be in [1, 1024]", shards);
   LR_CHECK_ARG(id_offset >= 0 && id_offset + N <= (int64_t(1) << 32) - 2, "flatip: id_offset + N must stay below 2^32");
-  LR_CHECK_ARG(out_scores || out_ids || out_keys, "flatip: no output requested");
-  const FlatipPlan& pl = make_plan(Q, N, k, d_used);
+  if (phases & RUN_REST) LR_CHECK_ARG(out_scores || out_ids || out_keys, "flatip: no output requested");
+  const FlatipPlan& pl = make_plan(Q, N, k, d_used, shards);
   if (!workspace || ws_bytes < pl.total_bytes || (uintptr_t(workspace) & 255)) {
     set_error("flatip: workspace too small or misaligned (%zu given, %zu needed, 256-byte aligned)", ws_bytes,
               pl.total_bytes);
@@ -459,15 +492,19 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
   prm.gthr = gthr;
   const ProfileEvents pe_saved = profile_events();
   uint64_t* carry = reinterpret_cast<uint64_t*>(ws + pl.off_carry);  // merged top-k so far: [q_pad][cap], k used
+  bool first_rest_pass = true;
   auto run_pass = [&](const PassPlan& pp, bool last) -> int {
     // carried top-k -> list slot `pp.splits` of the candidate array (+ thresholds), the pass, then the merge
     const int own_lists = pp.splits * pl.lmul;
     uint64_t* slot = cand + size_t(own_lists) * pl.q_pad * pl.cap;
     if (two_phase) {
+      // the exchanged k-th best of the whole prefix seeds the first pass after the exchange
+      const uint64_t* seed = first_rest_pass ? seed_keys : nullptr;
       carry_topk_kernel<<<unsigned(pl.q_pad), 128, 0, st>>>(carry, pl.cap, k, pl.q_pad, Q, slot, gthr,
-                                                            counts + size_t(own_lists) * pl.q_pad);
+                                                            counts + size_t(own_lists) * pl.q_pad, seed);
       LR_LAUNCH_CHECK();
     }
+    first_rest_pass = false;
     fill_params(prm, pl, pp, Q, N, d_used);
     if (pp.sched) {
       prm.team_ctr = reinterpret_cast<uint32_t*>(ws + pl.off_teamctr);
@@ -486,26 +523,69 @@ extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, in
     return topk_merge_two_level(cand, counts, lists, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0, nullptr, nullptr, carry,
                                 pl.cap, ws + pl.off_merge, pl.merge_bytes, st);
   };
-  if (two_phase) {
-    // ---- phase A: prefix -> merged top-k in `carry`
-    profile_events() = ProfileEvents{};
-    fill_params(prm, pl, pl.prefix, Q, N, d_used);
-    prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_pcounts);
-    prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_pcand);
-    LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
-    rc = launch_pass<EPI_TOPK>(pl, pl.prefix, tmA, tmB, prm, st);
-    if (!rc)
-      rc = topk_merge_two_level(prm.cand, prm.counts, pl.prefix.splits * pl.lmul, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0,
-                                nullptr, nullptr, carry, pl.cap, ws + pl.off_merge, pl.merge_bytes, st);
-    profile_events() = pe_saved;
-    if (rc) return rc;
-  } else if (!(debug & 2)) {  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)
-    LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
+  if (phases & RUN_PREFIX) {
+    if (two_phase) {
+      // ---- phase A: prefix -> merged top-k in `carry`
+      profile_events() = ProfileEvents{};
+      fill_params(prm, pl, pl.prefix, Q, N, d_used);
+      prm.counts = reinterpret_cast<int32_t*>(ws + pl.off_pcounts);
+      prm.cand = reinterpret_cast<uint64_t*>(ws + pl.off_pcand);
+      LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
+      rc = launch_pass<EPI_TOPK>(pl, pl.prefix, tmA, tmB, prm, st);
+      if (!rc)
+        rc = topk_merge_two_level(prm.cand, prm.counts, pl.prefix.splits * pl.lmul, Q, pl.q_pad, pl.cap, k, LR_SCORE_F32, 0,
+                                  nullptr, nullptr, carry, pl.cap, ws + pl.off_merge, pl.merge_bytes, st);
+      profile_events() = pe_saved;
+      if (rc) return rc;
+      if (prefix_keys_out)
+        LR_CUDA(cudaMemcpy2DAsync(prefix_keys_out, size_t(k) * 8, carry, size_t(pl.cap) * 8, size_t(k) * 8, size_t(Q),
+                                  cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (!(debug & 2)) {  // debug bit 1: keep the previous call's thresholds (perfect-threshold timing experiment)
+        LR_CUDA(cudaMemsetAsync(gthr, 0, size_t(pl.q_pad) * 4, st));
+      }
+      if (prefix_keys_out) LR_CUDA(cudaMemsetAsync(prefix_keys_out, 0, size_t(Q) * size_t(k) * 8, st));
+    }
+  }
+  if (!(phases & RUN_REST)) return LR_OK;
+  if (!two_phase && seed_keys) {  // single-phase plan of a sharded search: the seed is the only warm start
+    seed_thresholds_kernel<<<unsigned((Q + 255) / 256), 256, 0, st>>>(seed_keys, k, Q, gthr);
+    LR_LAUNCH_CHECK();
   }
   // ---- threshold-refresh passes (epilogue-bound searches only), then phase B / single phase
   for (int i = 0; i < pl.n_mid; ++i)
     if ((rc = run_pass(pl.mid[i], false))) return rc;
   return run_pass(pl.main, true);
+}
+
+extern "C" int lr_flatip_topk(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,
+                              int64_t d_used, const float* q_scale, const float* c_scale, int64_t id_offset, int k,
+                              float* out_scores, int64_t* out_ids, uint64_t* out_keys, void* workspace,
+                              size_t ws_bytes, void* stream) {
+  return flatip_run(RUN_PREFIX | RUN_REST, 1, q, ldq, corpus, ldc, Q, N, d_used, q_scale, c_scale, id_offset, k, nullptr,
+                    nullptr, out_scores, out_ids, out_keys, workspace, ws_bytes, stream);
+}
+
+extern "C" size_t lr_flatip_workspace_bytes_sharded(int64_t Q, int64_t N, int k, int64_t d_used, int n_shards) {
+  if (Q < 1 || N < 1 || k < 1 || d_used < 1 || n_shards < 1) return 0;
+  return make_plan(Q, N, k, d_used, n_shards).total_bytes;
+}
+
+extern "C" int lr_flatip_topk_begin(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,
+                                    int64_t d_used, const float* q_scale, const float* c_scale, int k, int n_shards,
+                                    uint64_t* out_prefix_keys, void* workspace, size_t ws_bytes, void* stream) {
+  LR_CHECK_ARG(out_prefix_keys, "flatip_topk_begin: null out_prefix_keys");
+  return flatip_run(RUN_PREFIX, n_shards, q, ldq, corpus, ldc, Q, N, d_used, q_scale, c_scale, 0, k, out_prefix_keys,
+                    nullptr, nullptr, nullptr, nullptr, workspace, ws_bytes, stream);
+}
+
+extern "C" int lr_flatip_topk_finish(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,
+                                     int64_t d_used, const float* q_scale, const float* c_scale, int64_t id_offset,
+                                     int k, int n_shards, const uint64_t* seed_keys, float* out_scores,
+                                     int64_t* out_ids, uint64_t* out_keys, void* workspace, size_t ws_bytes,
+                                     void* stream) {
+  return flatip_run(RUN_REST, n_shards, q, ldq, corpus, ldc, Q, N, d_used, q_scale, c_scale, id_offset, k, nullptr,
+                    seed_keys, out_scores, out_ids, out_keys, workspace, ws_bytes, stream);
 }
 
 extern "C" int lr_flatip_scores(const void* q, int64_t ldq, const void* corpus, int64_t ldc, int64_t Q, int64_t N,

@@ -208,10 +208,14 @@ class FlatIPIndex:
             index = cls(passage_embeddings.shape[1])
         if index.dim is None:
             index.dim = passage_embeddings.shape[1]
-        index.reserve(index.ntotal + len(passage_ids))
-        for start in range(0, len(passage_ids), buffer_size):
+        n_rows = passage_embeddings.shape[0]
+        if passage_ids is not None and len(passage_ids) != n_rows:
+            raise ValueError(f"{len(passage_ids)} passage ids for {n_rows} embeddings")
+        index.reserve(index.ntotal + n_rows)
+        for start in range(0, n_rows, buffer_size):
             index.add(passage_embeddings[start:start + buffer_size])
-        index._passage_ids = np.asarray(passage_ids, dtype=np.int64)
+        # passage_ids None: results are row positions (+ id_offset), the form chunk loops and shards exchange
+        index._passage_ids = None if passage_ids is None else np.asarray(passage_ids, dtype=np.int64)
         return index
 
     def _query(self, query_embeddings) -> torch.Tensor:
