@@ -161,8 +161,13 @@ int lr_flatip_plan_passes_sharded(int64_t Q, int64_t N, int k, int64_t d_used, i
                                   int max_passes, int64_t* out_flags2);
 
 /* Plan of the last lr_flatip_topk call on this thread (for bench / DESIGN):
- * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=rounds */
+ * out[0]=m_tiles out[1]=n_tiles out[2]=splits out[3]=band out[4]=cap out[5]=grid out[6]=units out[7]=warm-start prefix tiles (0 = single phase) */
 int lr_flatip_last_plan(int64_t* out8);
+/* The scoring passes of the last lr_flatip_topk / _begin / _finish call on this thread, rows as in lr_flatip_plan_passes
+ * (the last row is the main pass, the one lr_set_profile_events brackets); returns the number of passes. */
+int lr_flatip_last_plan_passes(int64_t* out_rows, int max_passes);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches is a difference of two reads). */
+unsigned long long lr_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------
  * Merge of candidate lists (per-split partials, per-shard top-k after the

@@ -36,6 +36,8 @@ PROTOTYPES = {
     "lr_flatip_plan_passes_sharded": (_i32, [_i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp]),
     "lr_flatip_scores": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "lr_flatip_last_plan": (_i32, [_vp]),
+    "lr_flatip_last_plan_passes": (_i32, [_vp, _i32]),
+    "lr_kernel_launches": (C.c_ulonglong, []),
     "lr_flatip_plan": (_i32, [_i64, _i64, _i32, _vp]),
     "lr_flatip_plan_passes": (_i32, [_i64, _i64, _i32, _i64, _vp, _i32, _vp]),
     "lr_set_profile_events": (_i32, [_vp, _vp]),

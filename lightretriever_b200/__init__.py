@@ -7,7 +7,7 @@ from . import _C  # noqa: F401  (ctypes binding; `_C.load()` builds/loads liblr_
 from .encode import (B200EmbeddingBag, construct_embedding_bag, emb_bag_inputs, flatten_token_ids, lasttoken_head,
                      tokenize_nonctx_qry_emb_bag)
 from .search import (FlatIPIndex, FlatIPSearch, decode_keys, drop_identical, encode_keys, flatip_scores, flatip_topk,
-                     merge_keys, topk_merge)
+                     flatip_topk_sharded, merge_keys, topk_merge)
 from .sharded import ShardedFlatIPIndex, ShardedImpactIndex, exchange_candidates, shard_range
 from .sparse_head import (aggregate, convert_sparse_reps_to_json, csr_to_json, get_sparse_attention_mask,
                           max_linear_mapping, sparse_head, sparsify_quantize)

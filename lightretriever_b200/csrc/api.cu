@@ -57,6 +57,9 @@ int ensure_dyn_smem(const void* func, int bytes) {
   return LR_OK;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 static std::atomic<unsigned> g_env_epoch{1};
 unsigned env_epoch() { return g_env_epoch.load(std::memory_order_acquire); }
 
@@ -78,6 +81,8 @@ extern "C" int lr_reload_env(void) {
   lr::g_env_epoch.fetch_add(1, std::memory_order_acq_rel);
   return LR_OK;
 }
+
+extern "C" unsigned long long lr_kernel_launches(void) { return lr::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* lr_last_error(void) { return lr::g_err; }
 extern "C" int lr_version(void) { return 100; }

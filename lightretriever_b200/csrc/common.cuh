@@ -35,9 +35,18 @@ void set_error(const char* fmt, ...);
       lr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return LR_ECUDA;                                                             \
     }                                                                              \
+    lr::count_launch();                                                            \
   } while (0)
 
+void count_launch();  // one per kernel this library launched (lr_kernel_launches); defined in api.cu
+
 int sm_count();  // cached per device
+
+// optional CUDA events recorded around the dominant kernel of a call (lr_set_profile_events)
+struct ProfileEvents {
+  cudaEvent_t begin = nullptr, end = nullptr;
+};
+ProfileEvents& profile_events();  // thread-local, defined in api.cu
 
 // Raises a kernel's dynamic shared-memory limit to at least `bytes`, once per (device, kernel).  The attribute belongs to
 // the function, not to a stream: setting it per launch with that launch's own size races between host threads (one

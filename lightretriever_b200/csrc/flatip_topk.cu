@@ -222,7 +222,7 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
   int main_begin = prefix_tiles;
   pl.n_mid = 0;
   const int refresh = env.refresh >= 0 ? env.refresh : (d_used <= 1024 ? 1 : 0);
-  if (refresh && pt_global >= 128 && prefix_tiles > 0 &&
+  if (refresh && pt_global >= 128 && prefix_tiles > 0 && prefix_splits_forced == 0 &&
       pt_global == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN)) {
     int growth = env.refresh_growth;
     if (growth < 2) growth = 2;
@@ -366,8 +366,8 @@ __global__ void carry_topk_kernel(const uint64_t* __restrict__ merged, int64_t k
                                   int32_t* __restrict__ counts, const uint64_t* __restrict__ seed) {
   const int64_t q = blockIdx.x;
   if (q >= q_pad) return;
-  if (q < Q)
-    for (int i = threadIdx.x; i < k; i += blockDim.x) dst[q * key_stride + i] = merged[q * key_stride + i];
+  __shared__ uint32_t s_g;
+  __shared__ int s_n;
   if (threadIdx.x == 0) {
     uint32_t g = 0;
     if (q < Q) {
@@ -379,8 +379,23 @@ __global__ void carry_topk_kernel(const uint64_t* __restrict__ merged, int64_t k
       }
     }
     gthr[q] = g;
-    counts[q] = q < Q ? k : 0;
+    s_g = g;
+    s_n = 0;
   }
+  __syncthreads();
+  if (q < Q) {
+    // the list is sorted: the entries that still reach the (possibly seeded) threshold are a leading run
+    const uint32_t g = s_g;
+    int n = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      const uint64_t key = merged[q * key_stride + i];
+      dst[q * key_stride + i] = key;
+      n += (key != 0ull && key_hi(key) >= g) ? 1 : 0;
+    }
+    if (n) atomicAdd(&s_n, n);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) counts[q] = q < Q ? s_n : 0;
 }
 
 // gthr[q] = max(gthr[q], score key of seed[q][k-1]) for a sharded search whose local plan has no warm-start pass
@@ -445,6 +460,23 @@ extern "C" int lr_flatip_plan_passes_sharded(int64_t Q, int64_t N, int k, int64_
 extern "C" int lr_flatip_plan_passes(int64_t Q, int64_t N, int k, int64_t d_used, int64_t* out_rows, int max_passes,
                                      int64_t* out_flags2) {
   return lr_flatip_plan_passes_sharded(Q, N, k, d_used, 1, out_rows, max_passes, out_flags2);
+}
+
+extern "C" int lr_flatip_last_plan_passes(int64_t* out_rows, int max_passes) {
+  LR_CHECK_ARG(out_rows && max_passes >= 1, "flatip_last_plan_passes: bad arguments");
+  const FlatipPlan& pl = g_last_plan;
+  int n = 0;
+  auto put = [&](const PassPlan& pp) {
+    if (n < max_passes) {
+      out_rows[4 * n + 0] = pp.tile_begin; out_rows[4 * n + 1] = pp.tile_end;
+      out_rows[4 * n + 2] = pp.splits; out_rows[4 * n + 3] = pp.sched;
+    }
+    ++n;
+  };
+  if (pl.prefix.units > 0) put(pl.prefix);
+  for (int i = 0; i < pl.n_mid; ++i) put(pl.mid[i]);
+  if (pl.main.units > 0) put(pl.main);
+  return n;
 }
 
 extern "C" int lr_flatip_last_plan(int64_t* out8) {

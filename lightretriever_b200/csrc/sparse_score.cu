@@ -722,6 +722,8 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   uint32_t* next3 = ctl + 3 * Q;
   p.overflow = next3 + 3;
   int rc = LR_OK;
+  const ProfileEvents pe = profile_events();  // lr_set_profile_events: bracket the scoring kernels (not the merge)
+  if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.begin, st));
   if (ss_bitmap()) {
     p.floor_q = ctl;
     p.next_unit = next3;
@@ -753,6 +755,7 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   p.warp_bytes = pl.warp_bytes[1];
   rc = ss_dispatch<int32_t>(p, pl, st);  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
   if (rc != LR_OK) return rc;
+  if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
   if (ss_env_int("LR_SPARSE_DEBUG")) {  // diagnostics: how much of the batch the bitmap kernel handed back
     uint32_t host[5] = {0, 0, 0, 0, 0};
     LR_CUDA(cudaStreamSynchronize(st));

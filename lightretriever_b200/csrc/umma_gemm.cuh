@@ -733,12 +733,6 @@ inline void plan_bands(int m_tiles, int band_max, int& band_size, int& n_bands) 
   n_bands = (m_tiles + band_size - 1) / band_size;
 }
 
-// optional CUDA events recorded around the main kernel (lr_set_profile_events)
-struct ProfileEvents {
-  cudaEvent_t begin = nullptr, end = nullptr;
-};
-ProfileEvents& profile_events();  // thread-local, defined in api.cu
-
 template <int EPI, int CL, bool PAIR = false, bool BIGLIST = false, bool WIDE = false>
 inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int grid,
                             cudaStream_t st) {
@@ -790,6 +784,7 @@ inline int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     set_error("kernel launch failed: %s (grid=%d cluster=%d)", cudaGetErrorString(e), grid, CL);
     return LR_ECUDA;
   }
+  count_launch();
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
   return LR_OK;
 }

@@ -35,14 +35,7 @@ logger = logging.getLogger(__name__)
 _WS = Workspace()
 
 
-def flatip_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, d_used: Optional[int] = None,
-                q_scale: Optional[torch.Tensor] = None, c_scale: Optional[torch.Tensor] = None,
-                id_offset: int = 0, return_keys: bool = False, workspace: Optional[Workspace] = None):
-    """scores, ids (and optionally sorted u64 keys) of the k largest ``query @ corpus.T`` per query.
-
-    query [Q, >=d_used] bf16, corpus [N, >=d_used] bf16, both on the same B200; rows may be strided views
-    (e.g. an MRL prefix ``x[:, :m]`` of full-width vectors) as long as the inner stride is 1.
-    """
+def _flatip_operands(query, corpus, d_used, q_scale, c_scale):
     q = require_cuda(query, "query")
     c = require_cuda(corpus, "corpus")
     if q.dtype != torch.bfloat16 or c.dtype != torch.bfloat16:
@@ -56,18 +49,30 @@ def flatip_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, d_used: Optio
     d = int(d_used) if d_used else min(q.shape[1], c.shape[1])
     if d_used is None and q.shape[1] != c.shape[1]:
         raise ValueError(f"dimension mismatch: query {q.shape[1]} vs corpus {c.shape[1]}")
-    Q, N = q.shape[0], c.shape[0]
     dev = q.device
     if c.device != dev:
         raise ValueError("query and corpus must be on the same device")
+    for name, s, n in (("q_scale", q_scale, q.shape[0]), ("c_scale", c_scale, c.shape[0])):
+        if s is not None and (s.dtype != torch.float32 or s.numel() != n or not s.is_contiguous() or s.device != dev):
+            raise ValueError(f"{name} must be a contiguous float32 tensor with {n} elements on {dev}")
+    return q, c, d, dev
+
+
+def flatip_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, d_used: Optional[int] = None,
+                q_scale: Optional[torch.Tensor] = None, c_scale: Optional[torch.Tensor] = None,
+                id_offset: int = 0, return_keys: bool = False, workspace: Optional[Workspace] = None):
+    """scores, ids (and optionally sorted u64 keys) of the k largest ``query @ corpus.T`` per query.
+
+    query [Q, >=d_used] bf16, corpus [N, >=d_used] bf16, both on the same B200; rows may be strided views
+    (e.g. an MRL prefix ``x[:, :m]`` of full-width vectors) as long as the inner stride is 1.
+    """
+    q, c, d, dev = _flatip_operands(query, corpus, d_used, q_scale, c_scale)
+    Q, N = q.shape[0], c.shape[0]
     lib = _C.load()
     ws = (workspace or _WS).get(lib.lr_flatip_workspace_bytes_for(Q, N, k, d), dev)
     scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
     ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
     keys = torch.empty((Q, k), dtype=torch.int64, device=dev) if return_keys else None
-    for name, s, n in (("q_scale", q_scale, Q), ("c_scale", c_scale, N)):
-        if s is not None and (s.dtype != torch.float32 or s.numel() != n or not s.is_contiguous() or s.device != dev):
-            raise ValueError(f"{name} must be a contiguous float32 tensor with {n} elements on {dev}")
     with torch.cuda.device(dev):
         _C.check(lib.lr_flatip_topk(
             q.data_ptr(), q.stride(0), c.data_ptr(), c.stride(0), Q, N, d,
@@ -75,6 +80,41 @@ def flatip_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, d_used: Optio
             int(id_offset), int(k), scores.data_ptr(), ids.data_ptr(),
             None if keys is None else keys.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
     return (scores, ids, keys) if return_keys else (scores, ids)
+
+
+def flatip_topk_sharded(query: torch.Tensor, corpus: torch.Tensor, k: int, n_shards: int, exchange,
+                        d_used: Optional[int] = None, q_scale: Optional[torch.Tensor] = None,
+                        c_scale: Optional[torch.Tensor] = None, id_offset: int = 0,
+                        workspace: Optional[Workspace] = None):
+    """One shard's part of a row-sharded search (Faiss ``shard=True``, faiss_index.py:60-70) with a SHARED warm start:
+    ``lr_flatip_topk_begin`` scores this shard's 1/n_shards of the warm-start prefix, ``exchange(prefix_keys [Q,k])``
+    returns the merged top-k keys of every shard's prefix (all-gather + ``lr_topk_merge``), and ``lr_flatip_topk_finish``
+    runs the remaining passes with the k-th best score of the whole prefix as the starting threshold.  Returns
+    (scores, ids, keys) of this shard; a row may hold fewer than k entries — only documents that can still reach the
+    global top-k are kept."""
+    q, c, d, dev = _flatip_operands(query, corpus, d_used, q_scale, c_scale)
+    Q, N = q.shape[0], c.shape[0]
+    lib = _C.load()
+    ws = (workspace or _WS).get(lib.lr_flatip_workspace_bytes_sharded(Q, N, k, d, int(n_shards)), dev)
+    scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    prefix_keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    qs = None if q_scale is None else q_scale.data_ptr()
+    cs = None if c_scale is None else c_scale.data_ptr()
+    with torch.cuda.device(dev):
+        _C.check(lib.lr_flatip_topk_begin(q.data_ptr(), q.stride(0), c.data_ptr(), c.stride(0), Q, N, d, qs, cs, int(k),
+                                          int(n_shards), prefix_keys.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          stream_ptr(dev)))
+        seed = exchange(prefix_keys)
+        if seed is not None:
+            if seed.shape != (Q, k) or seed.dtype != torch.int64 or not seed.is_contiguous() or seed.device != dev:
+                raise ValueError("exchange() must return contiguous int64 [Q, k] keys on the search device")
+        _C.check(lib.lr_flatip_topk_finish(q.data_ptr(), q.stride(0), c.data_ptr(), c.stride(0), Q, N, d, qs, cs,
+                                           int(id_offset), int(k), int(n_shards),
+                                           None if seed is None else seed.data_ptr(), scores.data_ptr(), ids.data_ptr(),
+                                           keys.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+    return scores, ids, keys
 
 
 def flatip_scores(query: torch.Tensor, corpus: torch.Tensor, d_used: Optional[int] = None) -> torch.Tensor:

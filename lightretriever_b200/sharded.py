@@ -69,19 +69,27 @@ class ShardedFlatIPIndex:
             self.local.add(emb)
 
     def search_keys(self, query, k: int, d_used: Optional[int] = None) -> torch.Tensor:
-        from .search import topk_merge
+        from .search import flatip_topk_sharded
 
         if self.local.ntotal != self.hi - self.lo:
             raise RuntimeError(f"shard incomplete: {self.local.ntotal} of {self.hi - self.lo} rows")
-        if self.hi == self.lo:  # more ranks than rows: this rank contributes empty lists
-            q_rows = query.shape[0]
-            keys = torch.zeros((q_rows, k), dtype=torch.int64, device=self.local.device)
-        else:
-            keys = self.local.search_keys(query, k, d_used=d_used)
         if self.world == 1:
-            return keys
+            return self.local.search_keys(query, k, d_used=d_used)
+        if self.hi == self.lo:  # more ranks than rows: this rank contributes empty lists to both exchanges
+            keys = torch.zeros((query.shape[0], k), dtype=torch.int64, device=self.local.device)
+            self._merge_across(keys)
+        else:
+            # shared warm start: every rank scores 1/world of the prefix; the k-th best of the union seeds all of them
+            keys = flatip_topk_sharded(self.local._query(query), self.local.corpus, k, self.world, self._merge_across,
+                                       d_used=d_used, id_offset=self.local.id_offset)[2]
+        return self._merge_across(keys)
+
+    def _merge_across(self, keys: torch.Tensor) -> torch.Tensor:
+        """all-gather of per-rank sorted keys [Q, k] + on-device merge -> the global sorted keys [Q, k] on every rank."""
+        from .search import topk_merge
+
         gathered = exchange_candidates(keys, self.group)  # [world, Q, k]
-        return topk_merge(gathered, k, return_keys=True)[2]
+        return topk_merge(gathered, keys.shape[1], return_keys=True)[2]
 
     def search_device(self, query, k: int, d_used: Optional[int] = None, return_keys: bool = False):
         from .search import decode_keys

@@ -77,49 +77,90 @@ class ImpactIndex:
         self._built = None
 
     def add_csr(self, indptr, tok, imp) -> None:
-        """Append documents given as doc-major CSR (numpy or torch, host or device)."""
+        """Append documents given as doc-major CSR (numpy or torch, host or device).  Staged as (lengths i32, tokens i32,
+        impacts i16 = the uint16 bit pattern): 6 bytes per posting, the size of the final index."""
         ip = torch.as_tensor(indptr).to(torch.int64)
-        tk = torch.as_tensor(tok).to(self.device, torch.int64)
+        tk = torch.as_tensor(tok).to(self.device)
         im = torch.as_tensor(imp).to(self.device)
-        if im.dtype == torch.int16:  # uint16 bit pattern from sparsify_quantize
-            im = im.to(torch.int32) & 0xFFFF
-        im = im.to(torch.int64)
         if tk.numel() and (int(tk.min()) < 0 or int(tk.max()) >= self.V):
             raise ValueError("token id out of range [0, vocab_size)")
-        if im.numel() and (int(im.min()) < 0 or int(im.max()) > 65535):
-            raise ValueError("impacts must fit uint16")
+        if im.dtype != torch.int16:  # int16 = uint16 bit pattern from sparsify_quantize, already in range
+            if im.numel() and (int(im.min()) < 0 or int(im.max()) > 65535):
+                raise ValueError("impacts must fit uint16")
+            im = im.to(torch.int32).to(torch.int16)  # two's-complement wrap keeps the low 16 bits
         n_docs = ip.numel() - 1
-        lens = (ip[1:] - ip[:-1]).to(self.device)
-        doc = torch.repeat_interleave(torch.arange(self.N, self.N + n_docs, device=self.device), lens)
-        self._doc_chunks.append((doc, tk, im))
+        lens = (ip[1:] - ip[:-1]).to(self.device, torch.int32)
+        if int(lens.sum()) != tk.numel() or tk.numel() != im.numel():
+            raise ValueError("indptr, tok and imp disagree on the number of postings")
+        self._doc_chunks.append((lens, tk.to(torch.int32).contiguous(), im.contiguous()))
         self.N += n_docs
         self._built = None
+
+    def add_dense_rows(self, tok: torch.Tensor, imp: torch.Tensor) -> None:
+        """Append documents given as fixed-width rows ``tok [n, w]`` / ``imp [n, w]`` (device tensors); a token repeated
+        inside a row keeps its first impact (a sparse vector has one weight per token)."""
+        tk = require_cuda(tok, "tok").to(torch.int32)
+        n, w = tk.shape
+        order = torch.sort(tk, dim=1, stable=True)
+        st = order.values
+        si = torch.gather(require_cuda(imp, "imp").to(torch.int32), 1, order.indices)
+        keep = torch.ones_like(st, dtype=torch.bool)
+        keep[:, 1:] = st[:, 1:] != st[:, :-1]
+        lens = keep.sum(dim=1)
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=tk.device)
+        indptr[1:] = torch.cumsum(lens, 0)
+        self.add_csr(indptr, st[keep], si[keep])
 
     def build(self):
         if self._built is not None:
             return self._built
         if self.N == 0:
             raise RuntimeError("index is empty")
-        doc = torch.cat([c[0] for c in self._doc_chunks])
-        tok = torch.cat([c[1] for c in self._doc_chunks])
-        imp = torch.cat([c[2] for c in self._doc_chunks])
-        # index-time (not the query path): stable sort by token keeps doc ids ascending inside a posting list
-        order = torch.argsort(tok, stable=True)
-        post_doc = doc[order].to(torch.int32).contiguous()
-        post_imp = imp[order].to(torch.int16).contiguous()  # uint16 bit pattern
-        counts = torch.bincount(tok, minlength=self.V)
-        post_indptr = torch.zeros(self.V + 1, dtype=torch.int64, device=self.device)
+        dev = self.device
+        # index time (not the query path): counting sort by token, one staged chunk at a time, so that the peak is the
+        # final index + the staged chunks (6 B per posting each) + one piece of scratch — 8.8M x 256 postings build on
+        # one GPU.  Chunks are visited in document order and sorted stably, so doc ids ascend inside a posting list.
+        counts = torch.zeros(self.V, dtype=torch.int64, device=dev)
+        for _, tk, _ in self._doc_chunks:
+            counts += torch.bincount(tk, minlength=self.V)
+        post_indptr = torch.zeros(self.V + 1, dtype=torch.int64, device=dev)
         post_indptr[1:] = torch.cumsum(counts, 0)
+        nnz = int(post_indptr[-1])
+        post_doc = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        post_imp = torch.empty(max(nnz, 1), dtype=torch.int16, device=dev)  # uint16 bit pattern
+        if nnz == 0:
+            post_doc.zero_()
+            post_imp.zero_()
+        cursor = post_indptr[:-1].clone()
+        doc0 = 0
+        piece = 1 << 25  # postings sorted per step
+        for lens, tk, im in self._doc_chunks:
+            n_docs = lens.numel()
+            ends = torch.cumsum(lens.to(torch.int64), 0)
+            for a in range(0, tk.numel(), piece):
+                e = min(a + piece, tk.numel())
+                t = tk[a:e]
+                # document of posting j = number of documents that end at or before j
+                doc = (torch.searchsorted(ends, torch.arange(a, e, device=dev), right=True) + doc0).to(torch.int32)
+                st = torch.sort(t, stable=True)
+                c = torch.bincount(t, minlength=self.V)
+                run_start = torch.cumsum(c, 0) - c
+                tl = st.values.long()
+                pos = cursor[tl] + (torch.arange(e - a, device=dev) - run_start[tl])
+                post_doc[pos] = doc[st.indices]
+                post_imp[pos] = im[a:e][st.indices]
+                cursor += c
+                del doc, st, c, run_start, tl, pos
+            doc0 += n_docs
+        # the staged rows stay (6 B per posting): a later add_csr() + build() re-sorts everything, as repeated
+        # AnseriniSearch.index() calls append to one collection (anserini_search.py:89-111)
         lib = _C.load()
         bd = lib.lr_sparse_block_docs()
         nblk = (self.N + bd - 1) // bd
-        blockptr = torch.empty(self.V * (nblk + 1), dtype=torch.int32, device=self.device)
-        if post_doc.numel() == 0:
-            post_doc = torch.zeros(1, dtype=torch.int32, device=self.device)
-            post_imp = torch.zeros(1, dtype=torch.int16, device=self.device)
-        with torch.cuda.device(self.device):
+        blockptr = torch.empty(self.V * (nblk + 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
             _C.check(lib.lr_sparse_build_blockptr(post_indptr.data_ptr(), post_doc.data_ptr(), self.V, self.N,
-                                                  blockptr.data_ptr(), stream_ptr(self.device)))
+                                                  blockptr.data_ptr(), stream_ptr(dev)))
         self._built = (post_indptr, post_doc, post_imp, blockptr)
         return self._built
 

@@ -42,6 +42,16 @@ def main():
     dist.broadcast(other, src=0)
     assert torch.equal(mine, other), "ranks disagree on the merged result"
 
+    # ---- the same with a warm-start pass in the plan: every rank scores 1/world of the prefix, the prefix top-k are
+    #      exchanged and the merged k-th best seeds all ranks (lr_flatip_topk_begin / _finish)
+    os.environ["LR_FLATIP_PREFIX_DOCS"] = "4096"
+    lr._C.reload_env()
+    s2, i2 = sh.search_device(q, k)
+    oracle.check_topk_parity(s2.cpu().numpy(), i2.cpu().numpy(), ref, k, rtol=1e-2)
+    assert torch.equal(i2, i) and torch.equal(s2, s), "shared warm start changed the result"
+    del os.environ["LR_FLATIP_PREFIX_DOCS"]
+    lr._C.reload_env()
+
     # ---- the searcher API: FlatIPSearch(use_multiple_gpu=True) == single-GPU searcher, chunked search() included
     cids = [f"doc-{j}" for j in range(3000)]
     qids = [f"q{j}" for j in range(20)]

@@ -731,6 +731,71 @@ def test_headline_regime_pairs_team_schedule_prefix_full_width(k):
     check(c2, inv[planted])
 
 
+@pytest.mark.parametrize("shards,prefix_docs,d", [(4, 4096, 128), (3, 2048, 256), (2, 0, 128)])
+def test_sharded_search_with_shared_warm_start_is_exact(monkeypatch, shards, prefix_docs, d):
+    """lr_flatip_topk_begin / _finish: every shard scores 1/shards of the warm-start prefix, the merged prefix top-k of all
+    shards seeds each shard's thresholds, and a shard keeps only documents that can still reach the GLOBAL top-k.  The
+    shards are played one after the other on one device (own workspaces); the merged result must equal the unsharded
+    oracle — with ties across shard boundaries, a shard that holds every winner of some queries and a shard that holds
+    none (its rows come back empty).  prefix_docs 0 = single-phase plan (the seed alone is the warm start)."""
+    monkeypatch.setenv("LR_FLATIP_PREFIX_DOCS", str(prefix_docs))
+    lr._C.reload_env()
+    from lightretriever_b200._util import Workspace
+    from lightretriever_b200.search import flatip_topk_sharded, merge_keys, decode_keys
+    gen = torch.Generator().manual_seed(shards * 100 + d)
+    Q, N, k = 300, 61_003, 50
+    q = F.normalize(torch.randn(Q, d, generator=gen), dim=-1).bfloat16()
+    c = F.normalize(torch.randn(N, d, generator=gen), dim=-1).bfloat16()
+    bounds = [N * r // shards for r in range(shards + 1)]
+    c[bounds[1] - 3:bounds[1] + 3] = c[9]                       # exact ties across a shard boundary
+    c[bounds[1] + 100:bounds[1] + 100 + 2 * k] = q[0]           # query 0: 2k identical winners, all in shard 1
+    qd, cd = q.cuda(), c.cuda()
+    ws = [Workspace() for _ in range(shards)]
+    pk, calls = [], []
+    for r in range(shards):
+        calls.append([])
+
+        def exch(prefix_keys, r=r):
+            calls[r].append(prefix_keys.clone())
+            return None
+        # first round: collect the prefix keys; finish(seed=None) must be a plain search of the shard
+        s_r, i_r, k_r = flatip_topk_sharded(qd, cd[bounds[r]:bounds[r + 1]], k, shards, exch, id_offset=bounds[r], workspace=ws[r])
+        es, ei = oracle.flatip_topk(q.float(), c[bounds[r]:bounds[r + 1]].float(), k, id_offset=bounds[r])
+        assert (ei == _np(i_r)).mean() > 0.999
+        pk.append(calls[r][0])
+    seed = merge_keys(pk, k)
+    if prefix_docs == 0:
+        assert all(bool((x == 0).all()) for x in pk)            # no warm-start pass in this plan: nothing to exchange
+        # play a seed from outside: the k-th best of the first 4000 documents of the whole corpus
+        seed = lr.flatip_topk(qd, cd[:4000], k, return_keys=True)[2]
+    ref = (q.float() @ c.float().T).numpy()
+    es, ei = oracle.flatip_topk(q.float(), c.float(), k)
+
+    def round_with(seed_keys):
+        finals, n_kept = [], []
+        for r in range(shards):
+            s_r, i_r, k_r = flatip_topk_sharded(qd, cd[bounds[r]:bounds[r + 1]], k, shards, lambda _: seed_keys,
+                                                id_offset=bounds[r], workspace=ws[r])
+            finals.append(k_r)
+            n_kept.append((i_r >= 0).sum(dim=1))
+            assert bool(((i_r == -1) == torch.isneginf(s_r)).all())
+        merged = merge_keys(finals, k)
+        gs, gi = decode_keys(merged)
+        oracle.check_topk_parity(_np(gs), _np(gi), ref, k, rtol=1e-2)
+        assert (ei == _np(gi)).mean() > 0.999
+        return merged, torch.stack(n_kept)
+
+    merged, _ = round_with(seed)
+    # The tightest valid seed is the global result itself: every shard then keeps only the global winners (and ties with
+    # the k-th score), rows of shards without a winner come back empty, and the merge still equals the oracle.
+    merged2, kept = round_with(merged)
+    assert torch.equal(merged2, merged)
+    assert int(kept.sum()) < Q * k + Q * 8 and bool((kept.sum(dim=0) >= k).all())
+    assert int(kept[1, 0]) == k and int(kept[:, 0].sum()) == k      # query 0: every winner lives in shard 1
+    monkeypatch.undo()
+    lr._C.reload_env()
+
+
 def test_faiss_flat_file_roundtrip_and_sharded_load(tmp_path):
     """Row f3: FlatIPSearch.save writes the reference's two files (<prefix>.flat.tsv + <prefix>.flat.faiss, an IndexFlatIP
     in Faiss's on-disk layout); load reads them straight into HBM — whole, or a row range (a rank's shard)."""
