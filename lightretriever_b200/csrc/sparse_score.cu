@@ -45,6 +45,8 @@ struct SSParams {
   const uint32_t* blockptr;
   int64_t V, N;
   int nblk, S, k, cap, warp_bytes;
+  int bd;             // documents per index block (blockptr granularity)
+  uint64_t* unit_thr;  // row kernel: [S][Q] final threshold key of each finished unit (0 = not finished), zeroed per launch
   uint64_t* cand;     // [S][Q][cap]
   int32_t* counts;    // [S][Q]
   uint32_t* floor_q;  // [Q] score floor of each query (k-th best score some unit has proven), zeroed per launch
@@ -120,6 +122,13 @@ __device__ __noinline__ uint64_t warp_cut_topk(uint64_t* list, uint32_t* n_io, i
   return kstar;
 }
 
+}  // namespace lr
+
+#include "sparse_rows.cuh"  // the default kernel (row-wise, no shared-memory atomics)
+
+namespace lr {
+
+// Round-1 kernel (LR_SPARSE_KERNEL=1): flattened posting slots + shared-memory atomics.  Kept for same-box A/B runs.
 template <int BD, int NB, typename AccT>
 __global__ void __launch_bounds__(SS_MAX_WARPS * 32, 1)
 sparse_score_kernel(const SSParams p) {
@@ -598,14 +607,32 @@ static int ss_env_int(const char* name) {
 }
 static bool ss_batch4() { static const bool v = ss_env_int("LR_SPARSE_BATCH") == 4; return v; }   // sweeps; default 8
 static bool ss_acc32_only() { static const bool v = ss_env_int("LR_SPARSE_ACC") == 32; return v; }  // A/B; default 16 + fallback
-// 2: bitmap kernel first, accumulator kernels for the units it hands back; 1 (default): accumulator kernels only
-static bool ss_bitmap() { static const bool v = ss_env_int("LR_SPARSE_KERNEL") == 2; return v; }
+// LR_SPARSE_KERNEL: 3 (default) row kernel (sparse_rows.cuh); 1 round-1 accumulator kernels (shared-memory atomics);
+// 2 bitmap kernel first, round-1 accumulator kernels for the units it hands back (negative result, kept for A/B)
+static int ss_kernel() {
+  static const int v = [] {
+    const int e = ss_env_int("LR_SPARSE_KERNEL");
+    return (e == 1 || e == 2) ? e : 3;
+  }();
+  return v;
+}
+static bool ss_bitmap() { return ss_kernel() == 2; }
+// accumulator bytes per worker of the row kernel: 16 / 32 / 64 KB = 8192 / 16384 / 32768 documents per step (16-bit)
+static int ss_rows_acc_kb() {
+  static const int v = [] {
+    const int e = ss_env_int("LR_SPARSE_STEP_KB");
+    return (e == 16 || e == 32 || e == 64) ? e : 32;
+  }();
+  return v;
+}
 
 struct SSPlan {
   int bd, nblk, S, cap;
+  bool rows;                    // row kernel: warps / warp_bytes / grid / smem [0] and [1] describe its two passes
+  int acc_bytes;                // row kernel: accumulator bytes per worker
   int warps[3], warp_bytes[3];  // [0] = 16-bit accumulators, [1] = int32 accumulators, [2] = bitmap kernel
   int grid[3];
-  size_t smem[3], off_counts, off_floor, off_redo, off_cand, off_merge, merge_bytes, total_bytes;
+  size_t smem[3], off_counts, off_floor, off_thr, off_redo, off_cand, off_merge, merge_bytes, total_bytes;
 };
 
 static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
@@ -615,17 +642,32 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   int cap = k + (k / 2 > 156 ? k / 2 : 156);  // k = 100 -> 256
   pl.cap = (cap + 31) / 32 * 32;
   const int G = sm_count();
+  pl.acc_bytes = ss_rows_acc_kb() * 1024;
+  // the row kernel steps over whole index blocks: its int32 pass needs acc_bytes / 4 >= block_docs
+  pl.rows = ss_kernel() == 3 && pl.acc_bytes / 4 >= pl.bd;
   for (int m = 0; m < 3; ++m) {
-    pl.warp_bytes[m] = m < 2 ? pl.bd * (m ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2
-                             : 2 * (pl.bd * S2_GROUP / 8) + S2_HASH * 8 + pl.cap * 8 + 256 * 4;
+    int max_warps = SS_MAX_WARPS;
+    if (pl.rows && m < 2) {
+      pl.warp_bytes[m] = pl.acc_bytes + 32 * 16 + pl.cap * 8 + 256 * 4 + 16;
+      max_warps = SR_MAX_WARPS;
+    } else {
+      pl.warp_bytes[m] = m < 2 ? pl.bd * (m ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2
+                               : 2 * (pl.bd * S2_GROUP / 8) + S2_HASH * 8 + pl.cap * 8 + 256 * 4;
+    }
     const int warps = int((size_t(227) * 1024 - 1024) / size_t(pl.warp_bytes[m]));
-    pl.warps[m] = warps > SS_MAX_WARPS ? SS_MAX_WARPS : warps;
+    pl.warps[m] = warps > max_warps ? max_warps : warps;
     pl.smem[m] = size_t(pl.warps[m]) * pl.warp_bytes[m];
   }
   const int64_t slots = int64_t(G) * pl.warps[ss_bitmap() ? 2 : (ss_acc32_only() ? 1 : 0)];
   // enough units to balance the dynamic hand-out (8 per warp), at most one unit per document block and at most 64
   // lists per query for the merge
   int64_t S = (8 * slots + Q - 1) / Q;
+  if (pl.rows) {
+    // The row kernel hands units out split-major, so the workers running together read the same slice of the index;
+    // more splits = a smaller slice (the posting runs of frequent terms stay in L2), as long as a unit keeps >= 4 steps.
+    const int64_t steps = (N + pl.acc_bytes / 2 - 1) / (pl.acc_bytes / 2);
+    if (S < steps / 4) S = steps / 4;
+  }
   if (S > 64) S = 64;
   if (S > pl.nblk) S = pl.nblk;
   if (S < 1) S = 1;
@@ -638,7 +680,10 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   pl.off_counts = 0;
   pl.off_floor = align(size_t(pl.S) * Q * 4);
-  pl.off_redo = align(pl.off_floor + 3 * size_t(Q) * 4 + 256);  // 3 x floor_q [Q], 3 unit counters, overflow flag, redo count
+  // 3 x floor_q [Q], 3 unit counters, overflow flag, redo count; then (row kernel) the finished-unit thresholds of its
+  // two passes, zeroed by the same memset
+  pl.off_thr = align(pl.off_floor + 3 * size_t(Q) * 4 + 256);
+  pl.off_redo = align(pl.off_thr + (pl.rows && pl.S > 1 ? 2 * size_t(units) * 8 : 0));
   pl.off_cand = align(pl.off_redo + size_t(units) * 4);          // units handed back by the bitmap kernel
   pl.off_merge = align(pl.off_cand + size_t(pl.S) * Q * pl.cap * 8);
   pl.merge_bytes = topk_merge_scratch_bytes(pl.S, Q, pl.cap, k);
@@ -681,6 +726,25 @@ static int ss_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
   return LR_OK;
 }
 
+template <int ACC_BYTES, typename AccT>
+static int sr_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  const int m = sizeof(AccT) == 4 ? 1 : 0;
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_rows_kernel<ACC_BYTES, AccT>), 227 * 1024);
+  if (rc) return rc;
+  sparse_score_rows_kernel<ACC_BYTES, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
+}
+
+template <typename AccT>
+static int sr_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  switch (pl.acc_bytes) {
+    case 16 * 1024: return sr_launch<16 * 1024, AccT>(p, pl, st);
+    case 64 * 1024: return sr_launch<64 * 1024, AccT>(p, pl, st);
+    default: return sr_launch<32 * 1024, AccT>(p, pl, st);
+  }
+}
+
 template <typename AccT>
 static int ss_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
   switch (pl.bd) {
@@ -713,12 +777,13 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   SSParams p{};
   p.q_indptr = q_indptr; p.q_tok = q_tok; p.q_cnt = q_cnt; p.Q = Q;
   p.post_indptr = post_indptr; p.post_doc = post_doc; p.post_imp = post_imp; p.blockptr = blockptr;
-  p.V = V; p.N = N; p.nblk = pl.nblk; p.S = pl.S; p.k = k; p.cap = pl.cap;
+  p.V = V; p.N = N; p.nblk = pl.nblk; p.S = pl.S; p.k = k; p.cap = pl.cap; p.bd = pl.bd;
   p.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   p.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   // control words: floor [3][Q] (bitmap / 16-bit / int32 pass) | next unit [3] | overflow | redo count
   uint32_t* ctl = reinterpret_cast<uint32_t*>(ws + pl.off_floor);
-  LR_CUDA(cudaMemsetAsync(ctl, 0, 3 * size_t(Q) * 4 + 5 * 4, st));
+  LR_CUDA(cudaMemsetAsync(ctl, 0, pl.off_redo - pl.off_floor, st));
+  uint64_t* unit_thr = (pl.rows && pl.S > 1) ? reinterpret_cast<uint64_t*>(ws + pl.off_thr) : nullptr;
   uint32_t* next3 = ctl + 3 * Q;
   p.overflow = next3 + 3;
   int rc = LR_OK;
@@ -745,7 +810,8 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
     p.floor_q = ctl + Q;
     p.next_unit = next3 + 1;
     p.warp_bytes = pl.warp_bytes[0];
-    rc = ss_dispatch<uint16_t>(p, pl, st);
+    p.unit_thr = unit_thr;
+    rc = pl.rows ? sr_dispatch<uint16_t>(p, pl, st) : ss_dispatch<uint16_t>(p, pl, st);
     if (rc != LR_OK) return rc;
   } else {
     p.overflow = nullptr;
@@ -753,7 +819,9 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   p.floor_q = ctl + 2 * Q;
   p.next_unit = next3 + 2;
   p.warp_bytes = pl.warp_bytes[1];
-  rc = ss_dispatch<int32_t>(p, pl, st);  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
+  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
+  p.unit_thr = unit_thr ? unit_thr + size_t(Q) * pl.S : nullptr;
+  rc = pl.rows ? sr_dispatch<uint32_t>(p, pl, st) : ss_dispatch<int32_t>(p, pl, st);
   if (rc != LR_OK) return rc;
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
   if (ss_env_int("LR_SPARSE_DEBUG")) {  // diagnostics: how much of the batch the bitmap kernel handed back
