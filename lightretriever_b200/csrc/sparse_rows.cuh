@@ -1,4 +1,4 @@
-// sparse_rows.cuh — K4, row kernel (default since round 2): the same gather-accumulate as sparse_score_kernel without a
+// sparse_rows.cuh — K4, row kernel (round 2; dense batches): the same gather-accumulate as sparse_score_kernel without a
 // single shared-memory atomic.
 //
 // Why: the accumulator kernel of round 1 issues one shared-memory atomicAdd per posting.  Scattered ATOMS retire at
@@ -20,7 +20,7 @@
 // list, no second walk: at the end of a step the accumulator block is cleared with 16-byte stores.
 //
 // Long posting runs (frequent terms: the Zipf head) take a second path: a batch of NB full rows of ONE term has no two
-// postings of the same document, so its NB read-modify-writes are issued as NB loads, NB adds, NB stores (no chain
+// postings of the same document, so its read-modify-writes are issued as loads, then adds, then stores (no chain
 // from row to row), the addresses come from one base pointer with immediate offsets, and one vote covers the batch.
 //
 // Units of one query are chained: unit (split s, query q) starts from the candidate list and threshold that unit
@@ -35,15 +35,15 @@
 namespace lr {
 
 constexpr int SR_NB = 8;          // rows whose loads are in flight together, per warp (x2: the next batch is issued first)
-constexpr int SR_MAX_WARPS = 12;  // workers per CTA (shared memory: acc + list + hist + table per warp)
+constexpr int SR_MAX_WARPS = 11;  // workers per CTA (shared memory: acc + list + hist + table per warp)
 
+// A batch of rows in flight.  General rows: doc = x[i], impact = x[NB + i], weight = x[2 NB + i] (0 for lanes past the
+// end of the run).  Long run (w != 0): NBF = 3 NB / 2 full rows of one term, doc = x[i], impact = x[NBF + i].
 template <int NB> struct RowBatch {
-  int doc[NB];
-  int imp[NB];
-  uint32_t wv[NB];  // general rows: term weight, 0 for lanes past the end of the run
-  int nb;           // rows in the batch (warp-uniform); 0 = no more work in this unit
-  int d0;           // first document of the step the batch belongs to
-  uint32_t w;       // != 0: NB full rows of one term with this weight (wv unused)
+  uint32_t x[3 * NB];
+  int nb;      // rows in the batch (warp-uniform); 0 = no more work in this unit
+  int d0;      // first document of the step the batch belongs to
+  uint32_t w;  // != 0: long-run batch of this weight
 };
 
 // Candidate list state of a worker (warp-uniform; shared memory, so that the candidate path can be an out-of-line call
@@ -142,7 +142,9 @@ template <int ACC_BYTES, typename AccT>
 __global__ void __launch_bounds__(SR_MAX_WARPS * 32, 1)
 sparse_score_rows_kernel(const SSParams p) {
   if (sizeof(AccT) == 4 && p.overflow && ld_relaxed_u32(p.overflow) == 0) return;  // the 16-bit pass was exact
+  if (ss_regime_skip(p)) return;  // a sparse batch (short posting runs) is the flat kernel's
   constexpr int NB = SR_NB;
+  constexpr int NBF = 3 * NB / 2;  // rows of a long-run batch (same registers: no per-lane weights)
   constexpr int STEP_DOCS = ACC_BYTES / int(sizeof(AccT));
   extern __shared__ __align__(16) uint8_t ss_smem[];
   const uint32_t full = 0xFFFFFFFFu;
@@ -291,18 +293,18 @@ sparse_score_rows_kernel(const SSParams p) {
         // long run: NB full rows of the term that owns row rL
         const uint32_t m = __ballot_sync(full, rp <= rL);  // lane 0 always votes; the highest voter owns the row
         const uint4 e = tab[31 - __clz(m)];
-        if (((int(e.z) + 1) >> 5) - rL >= NB) {  // warp-uniform
+        if (((int(e.z) + 1) >> 5) - rL >= NBF) {  // warp-uniform
           const int64_t idx = int64_t((uint64_t(e.y) << 32) | uint64_t(e.x)) + (rL * 32 + lane);
           const int32_t* pd = p.post_doc + idx;
           const uint16_t* pi = p.post_imp + idx;
 #pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            B.doc[i] = __ldg(pd + i * 32);
-            B.imp[i] = int(__ldg(pi + i * 32));
+          for (int i = 0; i < NBF; ++i) {
+            B.x[i] = uint32_t(__ldg(pd + i * 32));
+            B.x[NBF + i] = uint32_t(__ldg(pi + i * 32));
           }
           B.w = e.w;
-          B.nb = NB;
-          rL += NB;
+          B.nb = NBF;
+          rL += NBF;
           return;
         }
       }
@@ -317,9 +319,9 @@ sparse_score_rows_kernel(const SSParams p) {
           const int j = r * 32 + lane;
           const int last = int(e.z);
           const int64_t idx = int64_t((uint64_t(e.y) << 32) | uint64_t(e.x)) + min(j, last);  // lanes past the end repeat the last posting
-          B.doc[i] = __ldg(p.post_doc + idx);
-          B.imp[i] = int(__ldg(p.post_imp + idx));
-          B.wv[i] = j <= last ? e.w : 0u;
+          B.x[i] = uint32_t(__ldg(p.post_doc + idx));
+          B.x[NB + i] = uint32_t(__ldg(p.post_imp + idx));
+          B.x[2 * NB + i] = j <= last ? e.w : 0u;
         }
       }
       rL += B.nb;
@@ -340,42 +342,42 @@ sparse_score_rows_kernel(const SSParams p) {
       dirty = true;
       AccT* const ab = acc - B.d0;  // indexed by document id
       if (B.w != 0) {
-        // NB full rows of one term: no two postings share a document, so the read-modify-writes are independent
-        uint32_t old[NB], nw[NB];
+        // NBF full rows of one term: no two postings share a document, so the read-modify-writes are independent
+        uint32_t old[NBF], nw[NBF];
 #pragma unroll
-        for (int i = 0; i < NB; ++i) old[i] = uint32_t(ab[B.doc[i]]);
+        for (int i = 0; i < NBF; ++i) old[i] = uint32_t(ab[int(B.x[i])]);
         uint32_t hi_sc = 0;
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          nw[i] = old[i] + B.w * uint32_t(B.imp[i]);
+        for (int i = 0; i < NBF; ++i) {
+          nw[i] = old[i] + B.w * B.x[NBF + i];
           hi_sc = max(hi_sc, nw[i]);
           mxo |= nw[i];
         }
 #pragma unroll
-        for (int i = 0; i < NB; ++i) ab[B.doc[i]] = AccT(nw[i]);
+        for (int i = 0; i < NBF; ++i) ab[int(B.x[i])] = AccT(nw[i]);
         __syncwarp();
         if (__any_sync(full, hi_sc >= min_sc)) {
 #pragma unroll
-          for (int i = 0; i < NB; ++i)
+          for (int i = 0; i < NBF; ++i)
             if (__any_sync(full, nw[i] >= min_sc))
-              min_sc = sr_candidate(list, hist, st, floor_q, p.cap, p.k, nw[i], old[i], uint32_t(B.doc[i]));
+              min_sc = sr_candidate(list, hist, st, floor_q, p.cap, p.k, nw[i], old[i], B.x[i]);
         }
         return;
       }
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         if (i < B.nb) {  // warp-uniform
-          const uint32_t add = B.wv[i] * uint32_t(B.imp[i]);
+          const uint32_t add = B.x[2 * NB + i] * B.x[NB + i];
           uint32_t old = 0, nw = 0;
           if (add != 0) {
-            old = uint32_t(ab[B.doc[i]]);
+            old = uint32_t(ab[int(B.x[i])]);
             nw = old + add;
-            ab[B.doc[i]] = AccT(nw);
+            ab[int(B.x[i])] = AccT(nw);
             mxo |= nw;
           }
           __syncwarp();  // the next row may touch the same accumulators from other lanes
           if (__any_sync(full, nw >= min_sc))  // min_sc >= 1: idle lanes (nw == 0) never pass
-            min_sc = sr_candidate(list, hist, st, floor_q, p.cap, p.k, nw, old, uint32_t(B.doc[i]));
+            min_sc = sr_candidate(list, hist, st, floor_q, p.cap, p.k, nw, old, B.x[i]);
         }
       }
     };

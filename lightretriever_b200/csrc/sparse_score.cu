@@ -5,20 +5,26 @@
 // -pretokenized).  Score definition: scripts/asymmetric_sparse_infer.ipynb:207-228
 //     score(q, d) = sum_{t in q ∩ d} count_q(t) * impact_d(t)        (integer arithmetic)
 //
-// Gather-accumulate with warp-granular workers.  Documents are processed in blocks of SS_BLOCK_DOCS consecutive ids;
-// every WARP is an independent worker with its own int32 accumulator block, candidate list, histogram and touched
-// list in shared memory, so the kernel has no block-wide barrier at all and the dependent chain of one step
-// (block pointers -> postings -> shared-memory atomics -> visit) is hidden by the other resident warps.
-// A unit = (query, range of document blocks), handed out dynamically (one global atomic per unit).  Per step:
+// Two kernels, chosen per batch ON THE DEVICE from the batch's mean posting run (sparse_density_kernel; both are launched
+// and the one whose regime it is not returns at once):
+//   * row kernel (sparse_rows.cuh) for DENSE batches — long posting runs, the Zipf head: rows of 32 postings of one
+//     term, plain read-modify-write on warp-private accumulators, no shared-memory atomics;
+//   * flat kernel (below, the round-1 design) for SPARSE batches — runs much shorter than a row.
+// Common structure: gather-accumulate with warp-granular workers.  Documents are processed in blocks of SS_BLOCK_DOCS
+// consecutive ids; every WARP is an independent worker with its own accumulator block, candidate list and histogram in
+// shared memory, so neither kernel has a block-wide barrier and the dependent chain of one step (block pointers ->
+// postings -> accumulators -> candidates) is hidden by the other resident warps.  A unit = (query, range of document
+// blocks), handed out dynamically (one global atomic per unit).  Flat kernel, per step:
 //   1. lane t owns query term t and walks its row of blockptr with a two-block-ahead prefetch: the posting
 //      sub-range [blockptr[t][b], blockptr[t][b+1]) costs no search and no exposed latency;
-//   2. the sub-ranges are flattened (warp scan + shuffle binary search) and streamed in batches of
-//      SS_BATCH x 32 postings: all loads of a batch are issued before its shared-memory atomicAdds;
+//   2. the sub-ranges are flattened (warp scan + shuffle binary search) and streamed in batches of NB x 32 postings:
+//      all loads of a batch are issued before its shared-memory atomicAdds;
 //   3. the first add that finds 0 records the slot, so only touched accumulators are visited (a step touching more
 //      than SS_TOUCH_CAP slots scans the block); entries beating the unit's running 64-bit threshold key — and the
 //      query's global score floor, raised with atomicMax by every unit of that query — are appended to the warp's
 //      candidate list; a full list is cut to its exact top-k by a warp-level 64-bit radix select.
-// The unit's list goes to the workspace and the (two-level, for few queries) merge of topk_merge.cu produces the sorted result.  Integer-exact.
+// The unit's list goes to the workspace and the (two-level, for few queries) merge of topk_merge.cu produces the sorted
+// result.  Integer-exact; 16-bit accumulators with a 32-bit second pass when a sum would overflow.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -31,7 +37,6 @@ int topk_merge_two_level(const uint64_t* keys, const int32_t* counts, int L, int
 size_t topk_merge_scratch_bytes(int L, int64_t Q, int cap, int k);
 
 constexpr int SS_TOUCH_CAP = 512;  // touched-accumulator list per warp; a step that touches more scans the block
-constexpr int SS_BATCH = 4;        // postings per lane whose loads are in flight together
 constexpr int SS_MAX_WARPS = 20;
 
 struct SSParams {
@@ -52,13 +57,20 @@ struct SSParams {
   uint32_t* floor_q;  // [Q] score floor of each query (k-th best score some unit has proven), zeroed per launch
   uint32_t* next_unit;  // dynamic unit counter, zeroed per launch
   uint32_t* overflow;   // set by the 16-bit pass when an accumulator would exceed 65535; the 32-bit pass runs only then
-  // accumulator passes that follow the bitmap kernel (sparse_score_bitmap_kernel) work through the units it handed back
-  const uint32_t* unit_list;   // null: every unit
-  const uint32_t* unit_count;  // number of entries of unit_list (device memory)
-  // bitmap kernel only: where it records the units it does not finish itself
-  uint32_t* redo_units;
-  uint32_t* redo_count;
+  // regime dispatch: [0..1] = postings of all query terms of the batch (u64), [2] = number of query terms.  The batch is
+  // DENSE when the mean posting run per (term, step of the row kernel) reaches dense_thresh; a kernel whose `want_dense`
+  // disagrees returns at once.  Null: always run.
+  const uint32_t* regime;
+  uint32_t dense_thresh;
+  int want_dense;
 };
+
+__device__ __forceinline__ bool ss_regime_skip(const SSParams& p) {
+  if (!p.regime) return false;
+  const uint64_t postings = (uint64_t(p.regime[1]) << 32) | uint64_t(p.regime[0]);
+  const bool dense = postings >= uint64_t(p.dense_thresh) * uint64_t(p.regime[2]);
+  return dense != (p.want_dense != 0);
+}
 
 // Accumulator access.  AccT = uint16_t packs two documents per shared-memory word (twice the resident warps for the same
 // block size); a sum that would not fit raises `ovf` and the launch is repeated with int32 accumulators.
@@ -124,15 +136,17 @@ __device__ __noinline__ uint64_t warp_cut_topk(uint64_t* list, uint32_t* n_io, i
 
 }  // namespace lr
 
-#include "sparse_rows.cuh"  // the default kernel (row-wise, no shared-memory atomics)
+#include "sparse_rows.cuh"  // the row kernel (dense batches)
 
 namespace lr {
 
-// Round-1 kernel (LR_SPARSE_KERNEL=1): flattened posting slots + shared-memory atomics.  Kept for same-box A/B runs.
+// Flat kernel: flattened posting slots + shared-memory atomics (the round-1 design).  It serves SPARSE batches — short
+// posting runs, where a row of the row kernel would be mostly empty lanes — and stays selectable for same-box A/B runs.
 template <int BD, int NB, typename AccT>
 __global__ void __launch_bounds__(SS_MAX_WARPS * 32, 1)
 sparse_score_kernel(const SSParams p) {
   if (sizeof(AccT) == 4 && p.overflow && ld_relaxed_u32(p.overflow) == 0) return;  // the 16-bit pass was exact
+  if (ss_regime_skip(p)) return;
   extern __shared__ __align__(16) uint8_t ss_smem[];
   const uint32_t full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -146,16 +160,12 @@ sparse_score_kernel(const SSParams p) {
   for (int i = lane; i < BD; i += 32) acc[i] = 0;
   __syncwarp();
 
-  const uint32_t n_units = p.unit_list ? ld_relaxed_u32(p.unit_count) : uint32_t(p.Q * p.S);
+  const uint32_t n_units = uint32_t(p.Q * p.S);
   for (;;) {
     uint32_t u = 0;
-    if (lane == 0) {
-      u = atomicAdd(p.next_unit, 1u);
-      if (p.unit_list && u < n_units) u = p.unit_list[u];
-      else if (u >= n_units) u = 0xFFFFFFFFu;
-    }
+    if (lane == 0) u = atomicAdd(p.next_unit, 1u);
     u = __shfl_sync(full, u, 0);
-    if (u == 0xFFFFFFFFu) break;
+    if (u >= n_units) break;
     const int64_t q = u / uint32_t(p.S);
     const int s = int(u % uint32_t(p.S));
     const int b0 = int((int64_t(s) * p.nblk) / p.S);
@@ -348,228 +358,30 @@ sparse_score_kernel(const SSParams p) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Bitmap kernel (LR_SPARSE_KERNEL=2): the same warp-granular workers over steps of S2_GROUP blocks (32768 documents),
-// with TWO BITS per document instead of an accumulator.  Most documents a query touches are hit by exactly one of its
-// terms; their score is that one product and needs no accumulator at all.  Pass 1 streams the doc ids of the step and
-// marks `hit`; a second hit of the same document marks `multi` (and counts it).  Pass 2 streams (doc, impact) again
-// (L2 hits): a document without the `multi` bit is scored on the spot and tested against the thresholds; the others are
-// summed in a small open-addressing table (exact: their number is known from pass 1).  8x fewer steps than the
-// accumulator kernel for the same shared memory, so the per-step fixed work (pointer walk, scan, visit set-up) is
-// amortised over ~1000 postings instead of ~130.  Units it does not handle — queries with more than 32 terms, steps
-// with more than S2_HASH_MAX multi-hit documents (dense blocks) — are handed to the accumulator kernel through a list.
-constexpr int S2_GROUP = 8;        // index blocks per step
-constexpr int S2_HASH = 512;       // entries of the multi-hit table (per warp)
-constexpr int S2_HASH_MAX = 384;   // most multi-hit documents a step may have
-
-template <int BD>
-__global__ void __launch_bounds__(SS_MAX_WARPS * 32, 1)
-sparse_score_bitmap_kernel(const SSParams p) {
-  extern __shared__ __align__(16) uint8_t ss_smem[];
-  constexpr int W = BD * S2_GROUP / 32;  // bitmap words
-  const uint32_t full = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lt = lanemask_lt();
-  uint8_t* wbase = ss_smem + size_t(warp) * p.warp_bytes;
-  uint32_t* hit = reinterpret_cast<uint32_t*>(wbase);
-  uint32_t* multi = hit + W;
-  uint32_t* hkey = multi + W;
-  uint32_t* hval = hkey + S2_HASH;
-  uint64_t* list = reinterpret_cast<uint64_t*>(hval + S2_HASH);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(list + p.cap);
-
-  for (int i = lane; i < 2 * W + 2 * S2_HASH; i += 32) hit[i] = 0;
-  __syncwarp();
-
-  const uint32_t n_units = uint32_t(p.Q * p.S);
-  for (;;) {
-    uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(p.next_unit, 1u);
-    u = __shfl_sync(full, u, 0);
-    if (u >= n_units) break;
-    const int64_t q = u / uint32_t(p.S);
-    const int s = int(u % uint32_t(p.S));
-    const int b0 = int((int64_t(s) * p.nblk) / p.S);
-    const int b1 = int((int64_t(s + 1) * p.nblk) / p.S);
-    const int qt0 = p.q_indptr[q];
-    const int nterms = p.q_indptr[q + 1] - qt0;
-    bool handed_back = nterms > 32;  // warp-uniform
-    uint32_t n = 0;                  // entries in `list` (warp-uniform)
-    uint64_t thr = 0xFFFFFFFFull;    // candidates need key > thr; every score-0 key is <= this
-
-    auto append = [&](bool pass, uint64_t key) {
-      uint32_t pm = __ballot_sync(full, pass);
-      while (pm) {
-        const uint32_t room = uint32_t(p.cap) - n;
-        const uint32_t rank = __popc(pm & lt);
-        if (pass && rank < room) {
-          list[n + rank] = key;
-          pass = false;
-        }
-        n += min(uint32_t(__popc(pm)), room);
-        __syncwarp();
-        if (n == uint32_t(p.cap)) {
-          thr = warp_cut_topk(list, &n, p.k, hist);
-          if (p.S > 1 && lane == 0) atomicMax(p.floor_q + q, key_hi(thr));
-          pass = pass && key > thr;
-        }
-        pm = __ballot_sync(full, pass);
-      }
-    };
-
-    if (!handed_back) {
-      const uint32_t* bp_row = nullptr;
-      int64_t post_base = 0;
-      int my_w = 0;
-      uint32_t lo = 0, hi = 0, nxt = 0;
-      if (lane < nterms) {
-        const int t = p.q_tok[qt0 + lane];
-        const int w = p.q_cnt[qt0 + lane];
-        if (t >= 0 && t < p.V && w > 0) {  // terms with a count <= 0 contribute nothing
-          bp_row = p.blockptr + int64_t(t) * (p.nblk + 1);
-          post_base = p.post_indptr[t];
-          my_w = w;
-          lo = bp_row[b0];
-          hi = bp_row[min(b0 + S2_GROUP, b1)];
-          nxt = bp_row[min(b0 + 2 * S2_GROUP, b1)];
-        }
-      }
-      for (int b = b0; b < b1; b += S2_GROUP) {
-        const int d0 = b * BD;
-        const uint32_t floor_s = p.S > 1 ? ld_relaxed_u32(p.floor_q + q) : 0u;
-        int cnt = 0;
-        int64_t start = 0;
-        if (bp_row) {
-          start = post_base + lo;
-          cnt = int(hi - lo);
-          lo = hi;
-          hi = nxt;
-          if (b + 2 * S2_GROUP < b1) nxt = bp_row[min(b + 3 * S2_GROUP, b1)];  // consumed two steps from now
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const int t = __shfl_up_sync(full, incl, off);
-          if (lane >= off) incl += t;
-        }
-        const int total = __shfl_sync(full, incl, 31);
-        const int pre = incl - cnt;
-        const int64_t rel = start - pre;  // posting index of flattened position j inside this lane's term = rel + j
-        // largest l in [0, 32) with pre[l] <= j (lanes past the last term hold pre == total > j)
-        auto find_term = [&](int j) {
-          int l = 0;
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1) {
-            const int pv = __shfl_sync(full, pre, l + step);
-            if (pv <= j) l += step;
-          }
-          return l;
-        };
-        // ---- pass 1: hit / multi bits
-        uint32_t nmulti = 0;
-        for (int j0 = 0; j0 < total; j0 += 32 * SS_BATCH) {
-          int sl[SS_BATCH];
-#pragma unroll
-          for (int i = 0; i < SS_BATCH; ++i) {
-            sl[i] = -1;
-            if (j0 + i * 32 < total) {  // warp-uniform
-              const int j = min(j0 + i * 32 + lane, total - 1);
-              const int l = find_term(j);
-              const int64_t idx = __shfl_sync(full, rel, l) + j;
-              const int dsl = __ldg(p.post_doc + idx) - d0;
-              if (j0 + i * 32 + lane < total) sl[i] = dsl;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < SS_BATCH; ++i) {
-            if (j0 + i * 32 < total) {
-              bool newm = false;
-              if (sl[i] >= 0) {
-                const uint32_t bit = 1u << (sl[i] & 31);
-                const uint32_t old = atomicOr(&hit[sl[i] >> 5], bit);
-                if (old & bit) newm = (atomicOr(&multi[sl[i] >> 5], bit) & bit) == 0;
-              }
-              nmulti += __popc(__ballot_sync(full, newm));
-            }
-          }
-        }
-        __syncwarp();
-        if (nmulti > uint32_t(S2_HASH_MAX)) {
-          handed_back = true;  // dense step: the accumulator kernel redoes this unit
-        } else {
-          // ---- pass 2: single-hit documents are scored on the spot, multi-hit ones summed in the table
-          for (int j0 = 0; j0 < total; j0 += 32 * SS_BATCH) {
-            int sl[SS_BATCH], add[SS_BATCH];
-#pragma unroll
-            for (int i = 0; i < SS_BATCH; ++i) {
-              sl[i] = 0;
-              add[i] = 0;
-              if (j0 + i * 32 < total) {
-                const int j = min(j0 + i * 32 + lane, total - 1);
-                const int l = find_term(j);
-                const int64_t idx = __shfl_sync(full, rel, l) + j;
-                const int wl = __shfl_sync(full, my_w, l);
-                sl[i] = __ldg(p.post_doc + idx) - d0;
-                add[i] = j0 + i * 32 + lane < total ? wl * int(__ldg(p.post_imp + idx)) : 0;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < SS_BATCH; ++i) {
-              if (j0 + i * 32 < total) {
-                bool cand = false;
-                uint64_t key = 0;
-                if (add[i] > 0) {
-                  if ((multi[sl[i] >> 5] >> (sl[i] & 31)) & 1u) {
-                    const uint32_t kk = uint32_t(sl[i]) + 1u;
-                    uint32_t h = (uint32_t(sl[i]) * 2654435761u) >> 23;  // 9 bits
-                    for (;;) {
-                      const uint32_t old = atomicCAS(&hkey[h], 0u, kk);
-                      if (old == 0u || old == kk) {
-                        atomicAdd(&hval[h], uint32_t(add[i]));
-                        break;
-                      }
-                      h = (h + 1) & (S2_HASH - 1);
-                    }
-                  } else if (uint32_t(add[i]) >= floor_s) {
-                    key = make_key(uint32_t(add[i]), uint32_t(d0 + sl[i]));
-                    cand = key > thr;
-                  }
-                }
-                append(cand, key);
-              }
-            }
-          }
-          __syncwarp();
-          if (nmulti) {
-            for (int h0 = 0; h0 < S2_HASH; h0 += 32) {
-              const uint32_t kk = hkey[h0 + lane];
-              const uint32_t v = hval[h0 + lane];
-              if (kk) {
-                hkey[h0 + lane] = 0;
-                hval[h0 + lane] = 0;
-              }
-              const uint64_t key = make_key(v, uint32_t(d0) + kk - 1u);
-              append(kk != 0u && v > 0u && v >= floor_s && key > thr, key);
-            }
-          }
-        }
-        // ---- clear the bitmaps
-        __syncwarp();
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = lane; i < 2 * W / 4; i += 32) reinterpret_cast<uint4*>(hit)[i] = z;
-        __syncwarp();
-        if (handed_back) break;
+// Postings and terms of the whole query batch -> regime words (see SSParams::regime).  One thread per query.
+__global__ void sparse_density_kernel(const int32_t* __restrict__ q_indptr, const int32_t* __restrict__ q_tok,
+                                      const int32_t* __restrict__ q_cnt, int64_t Q, const int64_t* __restrict__ post_indptr,
+                                      int64_t V, uint32_t* regime) {
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  unsigned long long postings = 0;
+  uint32_t terms = 0;
+  if (q < Q) {
+    for (int i = q_indptr[q]; i < q_indptr[q + 1]; ++i) {
+      const int t = q_tok[i];
+      if (t >= 0 && t < V && q_cnt[i] > 0) {
+        postings += static_cast<unsigned long long>(post_indptr[t + 1] - post_indptr[t]);
+        ++terms;
       }
     }
-    if (handed_back) {
-      if (lane == 0) p.redo_units[atomicAdd(p.redo_count, 1u)] = u;
-      continue;
-    }
-    // ---- unit result
-    uint64_t* dst = p.cand + (int64_t(s) * p.Q + q) * p.cap;
-    for (uint32_t i = lane; i < n; i += 32) dst[i] = list[i];
-    if (lane == 0) p.counts[int64_t(s) * p.Q + q] = int32_t(n);
-    __syncwarp();
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
+    terms += __shfl_xor_sync(0xFFFFFFFFu, terms, off);
+  }
+  if ((threadIdx.x & 31) == 0 && terms) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(regime), postings);
+    atomicAdd(regime + 2, terms);
   }
 }
 
@@ -607,32 +419,42 @@ static int ss_env_int(const char* name) {
 }
 static bool ss_batch4() { static const bool v = ss_env_int("LR_SPARSE_BATCH") == 4; return v; }   // sweeps; default 8
 static bool ss_acc32_only() { static const bool v = ss_env_int("LR_SPARSE_ACC") == 32; return v; }  // A/B; default 16 + fallback
-// LR_SPARSE_KERNEL: 3 (default) row kernel (sparse_rows.cuh); 1 round-1 accumulator kernels (shared-memory atomics);
-// 2 bitmap kernel first, round-1 accumulator kernels for the units it hands back (negative result, kept for A/B)
+// LR_SPARSE_KERNEL: 0 / unset = by regime (dense batches: row kernel, sparse batches: flat kernel; decided on the device
+// from the batch's mean posting run, both kernels are launched and the other one returns at once);
+// 1 = flat kernel only; 3 = row kernel only
 static int ss_kernel() {
   static const int v = [] {
     const int e = ss_env_int("LR_SPARSE_KERNEL");
-    return (e == 1 || e == 2) ? e : 3;
+    return (e == 1 || e == 3) ? e : 0;
   }();
   return v;
 }
-static bool ss_bitmap() { return ss_kernel() == 2; }
+// mean postings per (query term, step) from which a batch counts as dense (a row holds 32)
+static int ss_dense_thresh() {
+  static const int v = [] {
+    const int e = ss_env_int("LR_SPARSE_DENSE_RUN");
+    return e > 0 ? e : 24;
+  }();
+  return v;
+}
 // accumulator bytes per worker of the row kernel: 16 / 32 / 64 KB = 8192 / 16384 / 32768 documents per step (16-bit)
 static int ss_rows_acc_kb() {
   static const int v = [] {
     const int e = ss_env_int("LR_SPARSE_STEP_KB");
-    return (e == 16 || e == 32 || e == 64) ? e : 32;
+    return (e == 16 || e == 32 || e == 64) ? e : 16;
   }();
   return v;
 }
 
 struct SSPlan {
-  int bd, nblk, S, cap;
-  bool rows;                    // row kernel: warps / warp_bytes / grid / smem [0] and [1] describe its two passes
-  int acc_bytes;                // row kernel: accumulator bytes per worker
-  int warps[3], warp_bytes[3];  // [0] = 16-bit accumulators, [1] = int32 accumulators, [2] = bitmap kernel
-  int grid[3];
-  size_t smem[3], off_counts, off_floor, off_thr, off_redo, off_cand, off_merge, merge_bytes, total_bytes;
+  int bd, nblk, cap;
+  bool rows, flat;  // which kernels a call launches
+  int acc_bytes;    // row kernel: accumulator bytes per worker
+  // [0] / [1] = flat kernel with 16-bit / int32 accumulators, [2] / [3] = row kernel with 16-bit / 32-bit accumulators
+  int warps[4], warp_bytes[4], grid[4];
+  size_t smem[4];
+  int S_flat, S_rows, S;  // splits per query of each kernel; S = the larger one = candidate lists per query
+  size_t off_counts, off_floor, off_thr, off_cand, off_merge, merge_bytes, total_bytes;
 };
 
 static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
@@ -643,52 +465,89 @@ static SSPlan ss_plan(int64_t Q, int64_t N, int k) {
   pl.cap = (cap + 31) / 32 * 32;
   const int G = sm_count();
   pl.acc_bytes = ss_rows_acc_kb() * 1024;
-  // the row kernel steps over whole index blocks: its int32 pass needs acc_bytes / 4 >= block_docs
-  pl.rows = ss_kernel() == 3 && pl.acc_bytes / 4 >= pl.bd;
-  for (int m = 0; m < 3; ++m) {
-    int max_warps = SS_MAX_WARPS;
-    if (pl.rows && m < 2) {
-      pl.warp_bytes[m] = pl.acc_bytes + 32 * 16 + pl.cap * 8 + 256 * 4 + 16;
-      max_warps = SR_MAX_WARPS;
-    } else {
-      pl.warp_bytes[m] = m < 2 ? pl.bd * (m ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2
-                               : 2 * (pl.bd * S2_GROUP / 8) + S2_HASH * 8 + pl.cap * 8 + 256 * 4;
-    }
+  // the row kernel steps over whole index blocks: its 32-bit pass needs acc_bytes / 4 >= block_docs
+  pl.rows = ss_kernel() != 1 && pl.acc_bytes / 4 >= pl.bd;
+  pl.flat = ss_kernel() != 3 || !pl.rows;
+  for (int m = 0; m < 4; ++m) {
+    const bool row = m >= 2;
+    pl.warp_bytes[m] = row ? pl.acc_bytes + 32 * 16 + pl.cap * 8 + 256 * 4 + 16
+                           : pl.bd * ((m & 1) ? 4 : 2) + pl.cap * 8 + 256 * 4 + SS_TOUCH_CAP * 2;
+    const int max_warps = row ? SR_MAX_WARPS : SS_MAX_WARPS;
     const int warps = int((size_t(227) * 1024 - 1024) / size_t(pl.warp_bytes[m]));
     pl.warps[m] = warps > max_warps ? max_warps : warps;
     pl.smem[m] = size_t(pl.warps[m]) * pl.warp_bytes[m];
   }
-  const int64_t slots = int64_t(G) * pl.warps[ss_bitmap() ? 2 : (ss_acc32_only() ? 1 : 0)];
   // enough units to balance the dynamic hand-out (8 per warp), at most one unit per document block and at most 64
   // lists per query for the merge
-  int64_t S = (8 * slots + Q - 1) / Q;
-  if (pl.rows) {
+  auto clampS = [&](int64_t S) {
+    if (S > 64) S = 64;
+    if (S > pl.nblk) S = pl.nblk;
+    return int(S < 1 ? 1 : S);
+  };
+  pl.S_flat = clampS((8 * int64_t(G) * pl.warps[ss_acc32_only() ? 1 : 0] + Q - 1) / Q);
+  {
     // The row kernel hands units out split-major, so the workers running together read the same slice of the index;
     // more splits = a smaller slice (the posting runs of frequent terms stay in L2), as long as a unit keeps >= 4 steps.
+    int64_t S = (8 * int64_t(G) * pl.warps[2] + Q - 1) / Q;
     const int64_t steps = (N + pl.acc_bytes / 2 - 1) / (pl.acc_bytes / 2);
     if (S < steps / 4) S = steps / 4;
+    pl.S_rows = clampS(S);
   }
-  if (S > 64) S = 64;
-  if (S > pl.nblk) S = pl.nblk;
-  if (S < 1) S = 1;
-  pl.S = int(S);
-  const int64_t units = Q * S;
-  for (int m = 0; m < 3; ++m) {
+  pl.S = !pl.rows ? pl.S_flat : (!pl.flat ? pl.S_rows : (pl.S_flat > pl.S_rows ? pl.S_flat : pl.S_rows));
+  for (int m = 0; m < 4; ++m) {
+    const int64_t units = Q * (m >= 2 ? pl.S_rows : pl.S_flat);
     const int64_t ctas = (units + pl.warps[m] - 1) / (pl.warps[m] > 0 ? pl.warps[m] : 1);
     pl.grid[m] = int(ctas < G ? ctas : G);
   }
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   pl.off_counts = 0;
+  // control block, zeroed per call together with the counts: floor_q [4][Q] (one per kernel pass), 4 unit counters,
+  // overflow flag, regime words; then (row kernel) the finished-unit thresholds of its two passes
   pl.off_floor = align(size_t(pl.S) * Q * 4);
-  // 3 x floor_q [Q], 3 unit counters, overflow flag, redo count; then (row kernel) the finished-unit thresholds of its
-  // two passes, zeroed by the same memset
-  pl.off_thr = align(pl.off_floor + 3 * size_t(Q) * 4 + 256);
-  pl.off_redo = align(pl.off_thr + (pl.rows && pl.S > 1 ? 2 * size_t(units) * 8 : 0));
-  pl.off_cand = align(pl.off_redo + size_t(units) * 4);          // units handed back by the bitmap kernel
+  pl.off_thr = align(pl.off_floor + 4 * size_t(Q) * 4 + 256);
+  pl.off_cand = align(pl.off_thr + (pl.rows && pl.S_rows > 1 ? 2 * size_t(Q) * pl.S_rows * 8 : 0));
   pl.off_merge = align(pl.off_cand + size_t(pl.S) * Q * pl.cap * 8);
   pl.merge_bytes = topk_merge_scratch_bytes(pl.S, Q, pl.cap, k);
   pl.total_bytes = align(pl.off_merge + pl.merge_bytes);
   return pl;
+}
+
+template <int BD, int NB, typename AccT>
+static int ss_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  const int m = sizeof(AccT) == 4 ? 1 : 0;
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_kernel<BD, NB, AccT>), 227 * 1024);
+  if (rc) return rc;
+  sparse_score_kernel<BD, NB, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
+}
+
+template <int ACC_BYTES, typename AccT>
+static int sr_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  const int m = sizeof(AccT) == 4 ? 3 : 2;
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_rows_kernel<ACC_BYTES, AccT>), 227 * 1024);
+  if (rc) return rc;
+  sparse_score_rows_kernel<ACC_BYTES, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
+}
+
+template <typename AccT>
+static int sr_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  switch (pl.acc_bytes) {
+    case 16 * 1024: return sr_launch<16 * 1024, AccT>(p, pl, st);
+    case 64 * 1024: return sr_launch<64 * 1024, AccT>(p, pl, st);
+    default: return sr_launch<32 * 1024, AccT>(p, pl, st);
+  }
+}
+
+template <typename AccT>
+static int ss_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
+  switch (pl.bd) {
+    case 2048: return ss_launch<2048, 4, AccT>(p, pl, st);
+    case 8192: return ss_launch<8192, 8, AccT>(p, pl, st);
+    default: return ss_batch4() ? ss_launch<4096, 4, AccT>(p, pl, st) : ss_launch<4096, 8, AccT>(p, pl, st);
+  }
 }
 
 }  // namespace lr
@@ -716,44 +575,6 @@ extern "C" size_t lr_sparse_score_workspace_bytes(int64_t Q, int64_t N, int k) {
   return ss_plan(Q, N, k).total_bytes;
 }
 
-template <int BD, int NB, typename AccT>
-static int ss_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
-  const int m = sizeof(AccT) == 4 ? 1 : 0;
-  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_kernel<BD, NB, AccT>), 227 * 1024);
-  if (rc) return rc;
-  sparse_score_kernel<BD, NB, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
-  LR_LAUNCH_CHECK();
-  return LR_OK;
-}
-
-template <int ACC_BYTES, typename AccT>
-static int sr_launch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
-  const int m = sizeof(AccT) == 4 ? 1 : 0;
-  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_rows_kernel<ACC_BYTES, AccT>), 227 * 1024);
-  if (rc) return rc;
-  sparse_score_rows_kernel<ACC_BYTES, AccT><<<pl.grid[m], pl.warps[m] * 32, pl.smem[m], st>>>(p);
-  LR_LAUNCH_CHECK();
-  return LR_OK;
-}
-
-template <typename AccT>
-static int sr_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
-  switch (pl.acc_bytes) {
-    case 16 * 1024: return sr_launch<16 * 1024, AccT>(p, pl, st);
-    case 64 * 1024: return sr_launch<64 * 1024, AccT>(p, pl, st);
-    default: return sr_launch<32 * 1024, AccT>(p, pl, st);
-  }
-}
-
-template <typename AccT>
-static int ss_dispatch(const SSParams& p, const SSPlan& pl, cudaStream_t st) {
-  switch (pl.bd) {
-    case 2048: return ss_launch<2048, 4, AccT>(p, pl, st);
-    case 8192: return ss_launch<8192, 8, AccT>(p, pl, st);
-    default: return ss_batch4() ? ss_launch<4096, 4, AccT>(p, pl, st) : ss_launch<4096, 8, AccT>(p, pl, st);
-  }
-}
-
 extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_tok, const int32_t* q_cnt, int64_t Q,
                                     const int64_t* post_indptr, const int32_t* post_doc, const uint16_t* post_imp,
                                     const uint32_t* blockptr, int64_t V, int64_t N, int64_t id_offset, int k,
@@ -767,7 +588,8 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   LR_CHECK_ARG(out_scores || out_ids || out_keys, "sparse_score: no output requested");
   SSPlan pl = ss_plan(Q, N, k);
   LR_CHECK_ARG(Q * int64_t(pl.S) < (int64_t(1) << 31), "sparse_score: too many (query, block range) units");
-  LR_CHECK_ARG(pl.warps[0] >= 1 && pl.warps[1] >= 1, "sparse_score: k (%d) leaves no shared memory for a worker", k);
+  for (int m = 0; m < 4; ++m)
+    LR_CHECK_ARG(pl.warps[m] >= 1, "sparse_score: k (%d) leaves no shared memory for a worker", k);
   if (!workspace || ws_bytes < pl.total_bytes || (uintptr_t(workspace) & 255)) {
     set_error("sparse_score: workspace too small or misaligned (%zu given, %zu needed)", ws_bytes, pl.total_bytes);
     return LR_EWORKSPACE;
@@ -777,59 +599,71 @@ extern "C" int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_to
   SSParams p{};
   p.q_indptr = q_indptr; p.q_tok = q_tok; p.q_cnt = q_cnt; p.Q = Q;
   p.post_indptr = post_indptr; p.post_doc = post_doc; p.post_imp = post_imp; p.blockptr = blockptr;
-  p.V = V; p.N = N; p.nblk = pl.nblk; p.S = pl.S; p.k = k; p.cap = pl.cap; p.bd = pl.bd;
+  p.V = V; p.N = N; p.nblk = pl.nblk; p.k = k; p.cap = pl.cap; p.bd = pl.bd;
   p.counts = reinterpret_cast<int32_t*>(ws + pl.off_counts);
   p.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
-  // control words: floor [3][Q] (bitmap / 16-bit / int32 pass) | next unit [3] | overflow | redo count
+  // counts (a kernel that sits the call out, or runs fewer splits, leaves empty lists) + control block + unit thresholds
+  LR_CUDA(cudaMemsetAsync(ws, 0, pl.off_cand, st));
   uint32_t* ctl = reinterpret_cast<uint32_t*>(ws + pl.off_floor);
-  LR_CUDA(cudaMemsetAsync(ctl, 0, pl.off_redo - pl.off_floor, st));
-  uint64_t* unit_thr = (pl.rows && pl.S > 1) ? reinterpret_cast<uint64_t*>(ws + pl.off_thr) : nullptr;
-  uint32_t* next3 = ctl + 3 * Q;
-  p.overflow = next3 + 3;
+  uint32_t* next4 = ctl + 4 * Q;
+  uint32_t* regime = next4 + 8;  // 8-byte aligned (off_floor is 256-aligned, 16 * Q + 32 bytes further)
+  p.overflow = next4 + 4;
   int rc = LR_OK;
   const ProfileEvents pe = profile_events();  // lr_set_profile_events: bracket the scoring kernels (not the merge)
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.begin, st));
-  if (ss_bitmap()) {
-    p.floor_q = ctl;
-    p.next_unit = next3;
-    p.warp_bytes = pl.warp_bytes[2];
-    p.redo_units = reinterpret_cast<uint32_t*>(ws + pl.off_redo);
-    p.redo_count = next3 + 4;
-    if (pl.bd != 4096) {
-      set_error("sparse_score: bitmap kernel needs block_docs 4096 (got %d)", pl.bd);
-      return LR_ECUDA;
-    }
-    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(sparse_score_bitmap_kernel<4096>), 227 * 1024))) return rc;
-    sparse_score_bitmap_kernel<4096><<<pl.grid[2], pl.warps[2] * 32, pl.smem[2], st>>>(p);
+  if (pl.rows && pl.flat) {
+    sparse_density_kernel<<<unsigned((Q + 255) / 256), 256, 0, st>>>(q_indptr, q_tok, q_cnt, Q, post_indptr, V, regime);
     LR_LAUNCH_CHECK();
-    p.unit_list = p.redo_units;   // the accumulator passes below only see what was handed back
-    p.unit_count = p.redo_count;
+    p.regime = regime;
+    const int64_t steps = (N + pl.acc_bytes / 2 - 1) / (pl.acc_bytes / 2);
+    p.dense_thresh = uint32_t(ss_dense_thresh() * steps);
   }
-  if (!ss_acc32_only()) {
-    // optimistic pass with 16-bit accumulators (exact unless a document's score would exceed 65535: flag -> pass 2)
-    p.floor_q = ctl + Q;
-    p.next_unit = next3 + 1;
-    p.warp_bytes = pl.warp_bytes[0];
-    p.unit_thr = unit_thr;
-    rc = pl.rows ? sr_dispatch<uint16_t>(p, pl, st) : ss_dispatch<uint16_t>(p, pl, st);
-    if (rc != LR_OK) return rc;
-  } else {
-    p.overflow = nullptr;
+  uint64_t* unit_thr = (pl.rows && pl.S_rows > 1) ? reinterpret_cast<uint64_t*>(ws + pl.off_thr) : nullptr;
+  // Per kernel: an optimistic pass with 16-bit accumulators (exact unless a document's score would exceed 65535: flag),
+  // then a pass with 32-bit accumulators that returns at once unless the flag is set (or LR_SPARSE_ACC=32).
+  if (pl.flat) {
+    p.S = pl.S_flat;
+    p.want_dense = 0;
+    p.unit_thr = nullptr;
+    if (!ss_acc32_only()) {
+      p.floor_q = ctl;
+      p.next_unit = next4;
+      p.warp_bytes = pl.warp_bytes[0];
+      if ((rc = ss_dispatch<uint16_t>(p, pl, st)) != LR_OK) return rc;
+    }
+    SSParams p2 = p;
+    if (ss_acc32_only()) p2.overflow = nullptr;
+    p2.floor_q = ctl + Q;
+    p2.next_unit = next4 + 1;
+    p2.warp_bytes = pl.warp_bytes[1];
+    if ((rc = ss_dispatch<int32_t>(p2, pl, st)) != LR_OK) return rc;
   }
-  p.floor_q = ctl + 2 * Q;
-  p.next_unit = next3 + 2;
-  p.warp_bytes = pl.warp_bytes[1];
-  // returns at once unless the overflow flag is set (or LR_SPARSE_ACC=32)
-  p.unit_thr = unit_thr ? unit_thr + size_t(Q) * pl.S : nullptr;
-  rc = pl.rows ? sr_dispatch<uint32_t>(p, pl, st) : ss_dispatch<int32_t>(p, pl, st);
-  if (rc != LR_OK) return rc;
+  if (pl.rows) {
+    p.S = pl.S_rows;
+    p.want_dense = 1;
+    if (!ss_acc32_only()) {
+      p.floor_q = ctl + 2 * Q;
+      p.next_unit = next4 + 2;
+      p.warp_bytes = pl.warp_bytes[2];
+      p.unit_thr = unit_thr;
+      if ((rc = sr_dispatch<uint16_t>(p, pl, st)) != LR_OK) return rc;
+    }
+    SSParams p2 = p;
+    if (ss_acc32_only()) p2.overflow = nullptr;
+    p2.floor_q = ctl + 3 * Q;
+    p2.next_unit = next4 + 3;
+    p2.warp_bytes = pl.warp_bytes[3];
+    p2.unit_thr = unit_thr ? unit_thr + size_t(Q) * pl.S_rows : nullptr;
+    if ((rc = sr_dispatch<uint32_t>(p2, pl, st)) != LR_OK) return rc;
+  }
   if (pe.begin && pe.end) LR_CUDA(cudaEventRecord(pe.end, st));
-  if (ss_env_int("LR_SPARSE_DEBUG")) {  // diagnostics: how much of the batch the bitmap kernel handed back
-    uint32_t host[5] = {0, 0, 0, 0, 0};
+  if (ss_env_int("LR_SPARSE_DEBUG")) {  // diagnostics: regime words and the overflow flag
+    uint32_t host[12] = {0};
     LR_CUDA(cudaStreamSynchronize(st));
-    LR_CUDA(cudaMemcpy(host, next3, sizeof(host), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "lr_b200 sparse_score: units %lld, handed back %u, 16-bit overflow %u\n", (long long)(Q * pl.S), host[4],
-            host[3]);
+    LR_CUDA(cudaMemcpy(host, next4, sizeof(host), cudaMemcpyDeviceToHost));
+    const uint32_t* rg = host + (regime - next4);
+    fprintf(stderr, "lr_b200 sparse_score: S flat %d rows %d, 16-bit overflow %u, batch postings %llu over %u terms, dense from %u\n",
+            pl.S_flat, pl.S_rows, host[4], (unsigned long long)((uint64_t(rg[1]) << 32) | rg[0]), rg[2], p.dense_thresh);
   }
   return topk_merge_two_level(p.cand, p.counts, pl.S, Q, Q, pl.cap, k, LR_SCORE_U32, id_offset, out_scores, out_ids,
                               out_keys, k, ws + pl.off_merge, pl.merge_bytes, st);

@@ -927,9 +927,13 @@ def test_online_searcher_graph_replay_matches_eager():
         srv.search(torch.zeros(9 * 32, dtype=torch.long).cuda(), torch.zeros(9, dtype=torch.long).cuda())
 
 
-def test_sparse_score_experimental_bitmap_kernel_is_exact():
-    """LR_SPARSE_KERNEL=2 (experimental, default off; see DESIGN K4): the bitmap kernel with hand-back of dense units and
-    long queries to the accumulator kernels must stay bit-exact.  The switch is read once per process -> subprocess."""
+@pytest.mark.parametrize("kernel,step_kb", [("1", "32"), ("3", "16"), ("3", "32"), ("3", "64")])
+def test_sparse_score_each_kernel_forced_is_exact(kernel, step_kb):
+    """The regime switch picks the row kernel (dense batches) or the flat kernel (sparse batches) per call; here each one is
+    FORCED (LR_SPARSE_KERNEL=1 flat / 3 rows, every step size of the row kernel) over the same index: head term present in
+    half of the documents (long runs: the batched full-row path), short runs, repeated query terms, a query of more than
+    32 terms (chunked steps), and weights that overflow the 16-bit accumulators (32-bit pass).  The switches are read
+    once per process -> subprocess."""
     import subprocess
     import sys
     code = r'''
@@ -945,17 +949,22 @@ for j in range(N):
     toks = rng.choice(V, size=int(rng.integers(0, 25)), replace=False)
     docs.append({str(int(t)): int(rng.integers(1, 400)) for t in toks})
 for j in range(0, N, 2):
-    docs[j]["5"] = int(rng.integers(1, 50))            # head term: dense steps are handed back
+    docs[j]["5"] = int(rng.integers(1, 50))            # head term: runs of thousands of postings per step
 queries = [" ".join(str(int(t)) for t in rng.integers(0, V, size=int(rng.integers(1, 33)))) for _ in range(40)]
 queries += ["5 6 7", "5 5 9 9 9", " ".join(str(t) for t in range(40))]   # head term, repeated terms, > 32 terms
 s = lr.ImpactSearch(vocab_size=V)
 s.index(docs, [str(j) for j in range(N)])
+dd = [{int(a): b for a, b in d.items()} for d in docs]
 qd = [oracle.query_counts([int(t) for t in q.split()]) for q in queries]
-es, ei = oracle.impact_topk(qd, [{int(a): b for a, b in d.items()} for d in docs], k)
+es, ei = oracle.impact_topk(qd, dd, k)
 gs, gi = s._ensure_index().search_device(*parse_queries(queries, V), k)
 assert (gi.cpu().numpy() == ei).all() and (gs.cpu().numpy() == es).all()
-print("bitmap kernel exact")
+wide = [{5: 3000, 6: 1, 7: 40000}, {int(t): int(rng.integers(1, 5000)) for t in rng.integers(0, V, size=20)}]
+es, ei = oracle.impact_topk(wide, dd, k)
+gs, gi = s._ensure_index().search_device(*parse_queries(wide, V), k)
+assert (gi.cpu().numpy() == ei).all() and (gs.cpu().numpy() == es).all()
+print("forced kernel exact")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, LR_SPARSE_KERNEL="2")
+    env = dict(os.environ, LR_SPARSE_KERNEL=kernel, LR_SPARSE_STEP_KB=step_kb)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "bitmap kernel exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "forced kernel exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

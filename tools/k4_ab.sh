@@ -1,7 +1,7 @@
 #!/bin/bash
 # K4 A/B on one box: parity tests of the sparse path, then c4 / c4uniform with the round-1 kernel and the row kernel
 mkdir -p gpurun_out/k4
-timeout 600 python -m pytest tests -m gpu -q -x -k "sparse_score or sparse_search or hybrid or smoke" 2>&1 | tail -4
+timeout 600 python -m pytest tests -m gpu -q -x -k "sparse or hybrid or impact" 2>&1 | tail -4
 IFS=","; for cfg in ${K4_CFGS:-3 16,3 32}; do IFS=" "
   kern=$(echo $cfg | cut -d' ' -f1); kb=$(echo $cfg | cut -d' ' -f2)
   for c in "c4uniform --docs 1100000" "c4 --docs 1100000 --steps 3" "c4uniform --docs 1100000 --queries 32" "c4 --docs 1100000 --queries 32"; do
