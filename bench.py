@@ -659,16 +659,16 @@ class SparseHeadWorkload:
             lens = torch.randint(16, self.S + 1, (self.B,), generator=gb, device=dev)
             mask = torch.arange(self.S, device=dev)[None] < lens[:, None]
             mask[:, 0] = False  # bos (get_sparse_attention_mask, sparse_pooling.py:23-41)
-            self.dev_batches.append((h, mask))
-            self.host_batches.append((h.cpu().pin_memory(), mask.cpu().pin_memory()))
-        self.valid_tokens = float(statistics.mean(float(m.sum()) for _, m in self.dev_batches))
+            self.dev_batches.append((h, mask, int(mask.sum())))  # the host owns the attention mask: it knows the count
+            self.host_batches.append((h.cpu().pin_memory(), mask.cpu().pin_memory(), int(mask.sum())))
+        self.valid_tokens = float(statistics.mean(float(m.sum()) for _, m, _ in self.dev_batches))
 
-    def step(self, h, mask, record=False):
-        return self.lr.sparse_head(h, self.W, None, mask, sparse_top_k=self.TOPK)
+    def step(self, h, mask, total, record=False):
+        return self.lr.sparse_head(h, self.W, None, mask, sparse_top_k=self.TOPK, valid_tokens=total)
 
     def step_e2e(self, i):
-        h, mask = self.host_batches[i % self.n_batches]
-        indptr, tok, imp = self.step(h.to(self.dev, non_blocking=True), mask.to(self.dev, non_blocking=True))
+        h, mask, total = self.host_batches[i % self.n_batches]
+        indptr, tok, imp = self.step(h.to(self.dev, non_blocking=True), mask.to(self.dev, non_blocking=True), total)
         self._host = (indptr.cpu(), tok.cpu(), imp.cpu())
 
     def io_bytes(self):
@@ -688,7 +688,7 @@ class SparseHeadWorkload:
 
     def valid_tokens_all(self):
         # every token up to a document's length is multiplied (the mask removes bos / eos / prompt afterwards)
-        return float(statistics.mean(float((m.float().cumsum(1).argmax(1) + 1).sum()) for _, m in self.dev_batches))
+        return float(statistics.mean(float((m.float().cumsum(1).argmax(1) + 1).sum()) for _, m, _ in self.dev_batches))
 
     def parity(self, res, batch_index, dist):
         """4 documents of the timed step against the fp32 oracle (max over valid tokens -> relu -> log1p -> top-k with ties
@@ -696,7 +696,7 @@ class SparseHeadWorkload:
         token sets equal outside the tie band."""
         torch = self.torch
         indptr, tok, imp = res
-        h, mask = self.dev_batches[batch_index]
+        h, mask, _ = self.dev_batches[batch_index]
         bad = {"impact_off": 0, "tokens_outside_band": 0}
         for b in (0, 1, self.B // 2, self.B - 1):
             hv = h[b][mask[b]].float()

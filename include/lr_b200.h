@@ -201,6 +201,21 @@ int lr_sparse_head_max(const void* hidden, const void* W, const float* bias, con
                        int64_t B, int64_t S, int64_t d, int64_t V, int relu, int log1p,
                        float* out /*[B,V]*/, void* stream);
 
+/* Packed form of the same operator: `hidden` holds ONLY the valid tokens, document after document ([T, d] bf16), and
+ * cu_seqlens [B+1] int32 (device) gives document b the rows [cu_seqlens[b], cu_seqlens[b+1]); T = cu_seqlens[B] is passed
+ * by the host (it knows the attention mask before the backbone runs).  Padding is never multiplied: the work is
+ * 2*T*d*V instead of 2*B*S*d*V.  The tokens are cut into balanced runs of whole 256-token tiles; a document that
+ * crosses a cut is finished by a small second kernel from the pieces the GEMM epilogue left in the workspace
+ * (device, 256-byte aligned, >= lr_sparse_head_packed_workspace_bytes(T, V)).  A document without a token gives
+ * finfo(bf16).min before relu, as above. */
+size_t lr_sparse_head_packed_workspace_bytes(int64_t T, int64_t V);
+int lr_sparse_head_max_packed(const void* hidden, const void* W, const float* bias, const int32_t* cu_seqlens,
+                              int64_t B, int64_t T, int64_t d, int64_t V, int relu, int log1p,
+                              float* out /*[B,V]*/, void* workspace, size_t ws_bytes, void* stream);
+/* hidden [B*S, d] bf16 + mask [B*S] uint8 -> packed [<= cap, d] (valid rows in order) and cu_seqlens [B+1] int32. */
+int lr_pack_tokens(const void* hidden, const uint8_t* mask, int64_t B, int64_t S, int64_t d, void* packed,
+                   int64_t cap, int32_t* cu_seqlens, void* stream);
+
 /* top_k_sampling (finetune/sparse_pooling.py:89-106: keep every entry >= the k_eff-th
  * largest, k_eff = min(max(top_k, min_keep), V), top_k <= 0 disables) followed by the
  * quantiser of convert_sparse_reps_to_json_pt (finetune/sparse_converter_mixin.py:103-160):

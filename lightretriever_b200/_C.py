@@ -48,6 +48,9 @@ PROTOTYPES = {
     "lr_fuse_topk_f64": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _i32, C.c_double, C.c_double, C.c_double, C.c_double,
                                 _vp, _vp, _vp, _vp]),
     "lr_sparse_head_max": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "lr_sparse_head_packed_workspace_bytes": (_sz, [_i64, _i64]),
+    "lr_sparse_head_max_packed": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "lr_pack_tokens": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "lr_sparsify_scratch_bytes": (_sz, [_i64, _i64]),
     "lr_sparsify_quantize": (_i32, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _vp]),
     "lr_sparse_block_docs": (_i32, []),

@@ -104,6 +104,18 @@ __global__ void exclusive_scan_kernel(const int32_t* cnt, int64_t B, int32_t* in
   }
 }
 
+// cu[0] = 0, cu[b] = lens[0] + ... + lens[b-1] where lens[b] arrives in cu[b + 1] (B is a batch size: one thread)
+__global__ void inclusive_scan_kernel(int32_t* cu, int64_t B) {
+  if (threadIdx.x == 0) {
+    int32_t run = 0;
+    cu[0] = 0;
+    for (int64_t b = 1; b <= B; ++b) {
+      run += cu[b];
+      cu[b] = run;
+    }
+  }
+}
+
 // ---- per document: ordered write of (token id, impact)
 __global__ void __launch_bounds__(SP_THREADS)
 sparsify_write_kernel(const float* __restrict__ reps, int64_t V, float quant, const float* thr_in,
@@ -148,27 +160,153 @@ sparsify_write_kernel(const float* __restrict__ reps, int64_t V, float quant, co
   }
 }
 
+// ---- packed tokens: documents that cross a split boundary
+// tiles [t0, t1) of split s (the same balanced ranges as umma_gemm.cuh split_cols)
+__device__ __forceinline__ void packed_split_range(int split, int splits, int64_t n_tiles, int64_t T, int64_t& c0, int64_t& c1) {
+  c0 = (int64_t(split) * n_tiles) / splits * BN;
+  c1 = (int64_t(split + 1) * n_tiles) / splits * BN;
+  if (c1 > T) c1 = T;
+}
+
+// split_doc0[s] = document holding the first token of split s (the first one that ends after it); 0 for split 0, whose
+// unit also emits the empty documents the batch may begin with
+__global__ void split_doc0_kernel(const int32_t* __restrict__ cu, int64_t B, int64_t T, int64_t n_tiles, int splits,
+                                  int32_t* split_doc0) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= splits) return;
+  int64_t c0, c1;
+  packed_split_range(s, splits, n_tiles, T, c0, c1);
+  int64_t lo = 0, hi = B - 1;  // smallest d with cu[d + 1] > c0
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (int64_t(cu[mid + 1]) > c0) hi = mid; else lo = mid + 1;
+  }
+  split_doc0[s] = s == 0 ? 0 : int32_t(lo);
+}
+
+// grid (splits - 1, row chunks): boundary b lies between split b - 1 and split b.  A document that crosses it was left
+// in pieces (GemmParams::edge); the CTA of the FIRST boundary a document crosses combines all of them.
+__global__ void __launch_bounds__(256)
+sparse_head_fix_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ split_doc0, const float* __restrict__ edge,
+                       int64_t rows, int64_t B, int64_t T, int64_t n_tiles, int splits, int relu, int log1p, float* out) {
+  const int b = blockIdx.x + 1;
+  int64_t c0, c1, p0, p1;
+  packed_split_range(b, splits, n_tiles, T, c0, c1);
+  packed_split_range(b - 1, splits, n_tiles, T, p0, p1);
+  const int64_t d = split_doc0[b];
+  const int64_t d_begin = cu[d], d_end = cu[d + 1];
+  if (d_begin >= c0) return;            // the document starts at the boundary: nothing crosses
+  if (b > 1 && d_begin < p0) return;    // it crossed an earlier boundary: that CTA's work
+  (void)B;
+  for (int64_t row = int64_t(blockIdx.y) * blockDim.x + threadIdx.x; row < rows; row += int64_t(gridDim.y) * blockDim.x) {
+    float acc = edge[(int64_t(b - 1) * 2 + 1) * rows + row];
+    for (int s = b; s < splits; ++s) {
+      acc = fmaxf(acc, edge[(int64_t(s) * 2 + 0) * rows + row]);
+      int64_t s0, s1;
+      packed_split_range(s, splits, n_tiles, T, s0, s1);
+      if (d_end <= s1) break;
+    }
+    float x = acc;
+    if (relu) x = fmaxf(x, 0.0f);
+    if (log1p) x = log1pf(x);
+    out[d * rows + row] = x;
+  }
+}
+
+// ---- packing: the valid tokens of every document, concatenated (what the packed GEMM multiplies)
+__global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t* __restrict__ mask, int64_t S, int32_t* lens) {
+  __shared__ int s_tot;
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x == 0) s_tot = 0;
+  __syncthreads();
+  int local = 0;
+  for (int64_t t = threadIdx.x; t < S; t += blockDim.x) local += mask[b * S + t] != 0;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, off);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_tot, local);
+  __syncthreads();
+  if (threadIdx.x == 0) lens[b] = s_tot;
+}
+
+// grid (B, PACK_SLICES): every CTA ranks the valid tokens of its document (warp 0, ballot scan) and its warps copy the
+// rows of one slice of the document, 16 bytes per lane
+constexpr int PACK_SLICES = 4;
+__global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t* __restrict__ hidden, const uint8_t* __restrict__ mask,
+                                                        int64_t S, int64_t row_bytes, const int32_t* __restrict__ cu_seqlens,
+                                                        uint8_t* __restrict__ packed, int64_t cap) {
+  extern __shared__ int32_t pk_pos[];  // [S]: destination row inside the document, -1 for masked tokens
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    int run = 0;
+    for (int64_t t0 = 0; t0 < S; t0 += 32) {
+      const int64_t t = t0 + lane;
+      const bool v = t < S && mask[b * S + t] != 0;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, v);
+      if (t < S) pk_pos[t] = v ? run + __popc(m & ((1u << lane) - 1u)) : -1;
+      run += __popc(m);
+    }
+  }
+  __syncthreads();
+  const int64_t base = cu_seqlens[b];
+  const int64_t per = (S + PACK_SLICES - 1) / PACK_SLICES;
+  const int64_t t_lo = int64_t(blockIdx.y) * per, t_hi = min(S, t_lo + per);
+  for (int64_t t = t_lo + warp; t < t_hi; t += blockDim.x / 32) {
+    const int pos = pk_pos[t];
+    if (pos < 0 || base + pos >= cap) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(hidden + (b * S + t) * row_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(packed + (base + pos) * row_bytes);
+    for (int64_t i = lane; i < row_bytes / 16; i += 32) dst[i] = ld_nc_v4(src + i);
+  }
+}
+
 }  // namespace lr
 
 using namespace lr;
 
-extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float* bias, const uint8_t* mask,
-                                  int64_t B, int64_t S, int64_t d, int64_t V, int relu, int log1p, float* out,
-                                  void* stream) {
-  LR_CHECK_ARG(hidden && W && mask && out, "sparse_head: null pointer");
-  LR_CHECK_ARG(B >= 1 && S >= 1 && V >= 1, "sparse_head: B, S, V must be >= 1");
-  LR_CHECK_ARG(d >= 8 && d % 8 == 0, "sparse_head: d (%lld) must be a positive multiple of 8", (long long)d);
-  LR_CHECK_ARG((uintptr_t(hidden) & 15) == 0 && (uintptr_t(W) & 15) == 0, "sparse_head: hidden/W must be 16-byte aligned");
-  LR_CHECK_ARG(B * S < (int64_t(1) << 31) - BN && V < (int64_t(1) << 31) - BM, "sparse_head: B*S or V too large");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// Packed tokens: splits = balanced ranges of whole tiles, ~2 tiles each and at most 64 of them (the edge buffer holds two
+// rows of V floats per split).
+struct PackedPlan {
+  int64_t n_tiles;
+  int splits;
+  size_t off_doc0, off_edge, total_bytes;  // workspace: team counters | split_doc0 | edge
+};
+static PackedPlan packed_plan(int64_t T, int64_t V) {
+  PackedPlan pp{};
+  pp.n_tiles = (T + BN - 1) / BN;
+  int64_t tps = (pp.n_tiles + 63) / 64;
+  if (tps < 2) tps = 2;
+  tps = env_int("LR_SPARSE_HEAD_TILES_PER_SPLIT", int(tps));  // tests: 1 = a cut every 256 tokens
+  if (tps < 1) tps = 1;
+  int64_t splits = (pp.n_tiles + tps - 1) / tps;
+  if (splits < 1) splits = 1;
+  pp.splits = int(splits);
+  pp.off_doc0 = 64 * 1024;  // team progress counters: n_bands * n_clusters words (<= 126 * 74)
+  pp.off_edge = pp.off_doc0 + ((size_t(pp.splits) * 4 + 255) / 256) * 256;
+  pp.total_bytes = pp.off_edge + size_t(pp.splits) * 2 * size_t(V) * 4;
+  return pp;
+}
+
+// cols = token rows of `hidden`; documents are seg_len tokens each (cu_seqlens == null) or the packed runs cu_seqlens
+// describes (mask == null then: every packed token is valid; `ws` = workspace of packed_plan())
+static int sparse_head_launch(const void* hidden, const void* W, const float* bias, const uint8_t* mask,
+                              const int32_t* cu_seqlens, int64_t B, int64_t S, int64_t cols, int64_t d, int64_t V, int relu,
+                              int log1p, float* out, uint8_t* ws, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
-  // a unit covers whole documents and at least ~2 column tiles
-  int sps = int((2 * BN + S - 1) / S);
-  if (sps < 1) sps = 1;
-  sps = env_int("LR_SPARSE_HEAD_DOCS_PER_UNIT", sps);
-  if (sps > B) sps = int(B);
-  const int splits = int((B + sps - 1) / sps);
+  int sps = 1, splits;
+  PackedPlan pp{};
+  if (cu_seqlens) {
+    pp = packed_plan(cols, V);
+    splits = pp.splits;
+  } else {
+    // a unit covers whole documents and at least ~2 column tiles
+    sps = int((2 * BN + S - 1) / S);
+    if (sps < 1) sps = 1;
+    sps = env_int("LR_SPARSE_HEAD_DOCS_PER_UNIT", sps);
+    if (sps > B) sps = int(B);
+    splits = int((B + sps - 1) / sps);
+  }
   // Vocabulary bands x document splits.  With enough of both, fixed teams of clusters walk the splits of a band in step
   // (umma_gemm.cuh for_each_unit): a hidden-state tile is fetched from HBM once per team and the band's lm_head rows
   // stay L2-resident; the team schedule runs as cta_group::2 pairs.  Otherwise round robin over 12-tile bands.
@@ -182,15 +320,25 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   }
   const GemmGeometry geo = plan_geometry(V, env_int("LR_SPARSE_HEAD_BAND", 12), mode);
   if ((rc = make_tmap(&tmA, W, V, d, d, BM))) return rc;
-  if ((rc = make_tmap(&tmB, hidden, B * S, d, d, BN / geo.cl))) return rc;
+  if ((rc = make_tmap(&tmB, hidden, cols, d, d, BN / geo.cl))) return rc;
   GemmParams prm{};
-  prm.rows = V; prm.cols = B * S;
+  prm.rows = V; prm.cols = cols;
   prm.m_tiles = geo.m_tiles; prm.m_groups = geo.m_groups;
   prm.row_pad = int64_t(prm.m_tiles) * BM;
   prm.kblocks = int((d + BK - 1) / BK);
   prm.seg_len = S; prm.n_segs = B;
   prm.segs_per_split = sps;
   prm.splits = splits;
+  if (cu_seqlens) {
+    prm.cu_seqlens = cu_seqlens;
+    prm.n_tiles = int(pp.n_tiles);
+    prm.tile_begin = 0;
+    prm.split_doc0 = reinterpret_cast<const int32_t*>(ws + pp.off_doc0);
+    prm.edge = reinterpret_cast<float*>(ws + pp.off_edge);
+    split_doc0_kernel<<<(splits + 127) / 128, 128, 0, st>>>(cu_seqlens, B, cols, pp.n_tiles, splits,
+                                                          reinterpret_cast<int32_t*>(ws + pp.off_doc0));
+    LR_LAUNCH_CHECK();
+  }
   prm.band_size = geo.band_size; prm.n_bands = geo.n_bands;
   prm.units = prm.m_groups * prm.splits;
   prm.bias = bias; prm.mask = mask; prm.out = out; prm.relu = relu; prm.log1p = log1p;
@@ -198,18 +346,25 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   prm.policy_b = l2_policy(env_int("LR_SPARSE_HEAD_POLICY_B", 0));
   int clusters = prm.units < geo.n_clusters ? prm.units : geo.n_clusters;
   uint32_t* team_ctr = nullptr;
+  bool own_ctr = false;
   if (team_band > 0 && geo.cl == 2) {
     prm.sched = 1;
     prm.team_window = env_int("LR_SPARSE_HEAD_TEAM_WINDOW", 1);
     prm.band_size = team_band;
     prm.n_bands = (prm.m_groups + team_band - 1) / team_band;
     clusters = geo.n_clusters;
-    // progress counters of the teams, one per (band, team): stream-ordered scratch, released after the launch
+    // progress counters of the teams, one per (band, team): the head of the caller's workspace (packed entry point), or
+    // stream-ordered scratch released after the launch
     const size_t ctr_bytes = size_t(prm.n_bands) * size_t(geo.n_clusters) * 4;
-    LR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&team_ctr), ctr_bytes, st));
+    if (ws && ctr_bytes <= pp.off_doc0) {
+      team_ctr = reinterpret_cast<uint32_t*>(ws);
+    } else {
+      LR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&team_ctr), ctr_bytes, st));
+      own_ctr = true;
+    }
     cudaError_t e = cudaMemsetAsync(team_ctr, 0, ctr_bytes, st);
     if (e != cudaSuccess) {
-      cudaFreeAsync(team_ctr, st);
+      if (own_ctr) cudaFreeAsync(team_ctr, st);
       set_error("sparse_head: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
       return LR_ECUDA;
     }
@@ -219,8 +374,69 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
   if (geo.pair) rc = launch_umma_gemm<EPI_MAXTOK, 2, true>(tmA, tmB, prm, grid, st);
   else rc = geo.cl == 2 ? launch_umma_gemm<EPI_MAXTOK, 2>(tmA, tmB, prm, grid, st)
                         : launch_umma_gemm<EPI_MAXTOK, 1>(tmA, tmB, prm, grid, st);
-  if (team_ctr) cudaFreeAsync(team_ctr, st);
+  if (own_ctr) cudaFreeAsync(team_ctr, st);
+  if (rc == LR_OK && cu_seqlens && splits > 1) {
+    int chunks = int((V + 255) / 256);
+    if (chunks > 64) chunks = 64;
+    sparse_head_fix_kernel<<<dim3(unsigned(splits - 1), unsigned(chunks)), 256, 0, st>>>(
+        cu_seqlens, prm.split_doc0, prm.edge, V, B, cols, pp.n_tiles, splits, relu, log1p, out);
+    LR_LAUNCH_CHECK();
+  }
   return rc;
+}
+
+extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float* bias, const uint8_t* mask,
+                                  int64_t B, int64_t S, int64_t d, int64_t V, int relu, int log1p, float* out,
+                                  void* stream) {
+  LR_CHECK_ARG(hidden && W && mask && out, "sparse_head: null pointer");
+  LR_CHECK_ARG(B >= 1 && S >= 1 && V >= 1, "sparse_head: B, S, V must be >= 1");
+  LR_CHECK_ARG(d >= 8 && d % 8 == 0, "sparse_head: d (%lld) must be a positive multiple of 8", (long long)d);
+  LR_CHECK_ARG((uintptr_t(hidden) & 15) == 0 && (uintptr_t(W) & 15) == 0, "sparse_head: hidden/W must be 16-byte aligned");
+  LR_CHECK_ARG(B * S < (int64_t(1) << 31) - BN && V < (int64_t(1) << 31) - BM, "sparse_head: B*S or V too large");
+  return sparse_head_launch(hidden, W, bias, mask, nullptr, B, S, B * S, d, V, relu, log1p, out, nullptr,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t lr_sparse_head_packed_workspace_bytes(int64_t T, int64_t V) {
+  if (T < 1 || V < 1) return 0;
+  return packed_plan(T, V).total_bytes;
+}
+
+extern "C" int lr_sparse_head_max_packed(const void* hidden, const void* W, const float* bias, const int32_t* cu_seqlens,
+                                         int64_t B, int64_t T, int64_t d, int64_t V, int relu, int log1p, float* out,
+                                         void* workspace, size_t ws_bytes, void* stream) {
+  LR_CHECK_ARG(hidden && W && cu_seqlens && out, "sparse_head_packed: null pointer");
+  LR_CHECK_ARG(B >= 1 && T >= 1 && V >= 1, "sparse_head_packed: B, T, V must be >= 1");
+  LR_CHECK_ARG(d >= 8 && d % 8 == 0, "sparse_head_packed: d (%lld) must be a positive multiple of 8", (long long)d);
+  LR_CHECK_ARG((uintptr_t(hidden) & 15) == 0 && (uintptr_t(W) & 15) == 0, "sparse_head_packed: hidden/W must be 16-byte aligned");
+  LR_CHECK_ARG(T < (int64_t(1) << 31) - BN && V < (int64_t(1) << 31) - BM, "sparse_head_packed: T or V too large");
+  const size_t need = packed_plan(T, V).total_bytes;
+  if (!workspace || ws_bytes < need || (uintptr_t(workspace) & 255)) {
+    set_error("sparse_head_packed: workspace too small or misaligned (%zu given, %zu needed)", ws_bytes, need);
+    return LR_EWORKSPACE;
+  }
+  return sparse_head_launch(hidden, W, bias, nullptr, cu_seqlens, B, 0, T, d, V, relu, log1p, out,
+                            static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lr_pack_tokens(const void* hidden, const uint8_t* mask, int64_t B, int64_t S, int64_t d, void* packed,
+                              int64_t cap, int32_t* cu_seqlens, void* stream) {
+  LR_CHECK_ARG(hidden && mask && packed && cu_seqlens, "pack_tokens: null pointer");
+  LR_CHECK_ARG(B >= 1 && S >= 1 && d >= 8 && d % 8 == 0, "pack_tokens: bad sizes");
+  LR_CHECK_ARG(B <= 65535 * 32 && S * 4 <= 200 * 1024, "pack_tokens: B or S too large");
+  LR_CHECK_ARG((uintptr_t(hidden) & 15) == 0 && (uintptr_t(packed) & 15) == 0, "pack_tokens: buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // lengths into cu_seqlens[1..B], then an in-place scan (cu_seqlens[0] = 0)
+  pack_count_kernel<<<unsigned(B), 256, 0, st>>>(mask, S, cu_seqlens + 1);
+  LR_LAUNCH_CHECK();
+  inclusive_scan_kernel<<<1, 32, 0, st>>>(cu_seqlens, B);
+  LR_LAUNCH_CHECK();
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(pack_rows_kernel), 200 * 1024);
+  if (rc) return rc;
+  pack_rows_kernel<<<dim3(unsigned(B), PACK_SLICES), 256, size_t(S) * 4, st>>>(
+      static_cast<const uint8_t*>(hidden), mask, S, d * 2, cu_seqlens, static_cast<uint8_t*>(packed), cap);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
 }
 
 extern "C" size_t lr_sparsify_scratch_bytes(int64_t B, int64_t V) {

@@ -95,6 +95,14 @@ struct GemmParams {
   int64_t seg_len;      // EPI_MAXTOK: tokens per document (S); split = segs_per_split documents
   int64_t n_segs;
   int segs_per_split;
+  // EPI_MAXTOK, packed tokens (cu_seqlens != null): document b = columns [cu_seqlens[b], cu_seqlens[b+1]).  Splits are
+  // balanced ranges of whole 256-token tiles (n_tiles / tile_begin as for the top-k epilogue), so a document can start in
+  // one split and end in another: split_doc0[s] = the document holding the first token of split s (0 for s = 0), and a
+  // unit leaves the running max of such a document's piece in edge[(2 s + which) * rows + row] — which = 0 for a
+  // document that began before the split, 1 for one that goes on after it — for sparse_head_fix_kernel to combine.
+  const int32_t* cu_seqlens;
+  const int32_t* split_doc0;
+  float* edge;
   // EPI_TOPK
   int k, cap;
   const float* q_scale;
@@ -144,7 +152,7 @@ __device__ __forceinline__ void for_each_unit(const GemmParams& p, int cluster_i
 // columns [c0, c1) covered by a split; tiles start at c0 and step BN
 template <int EPI>
 __device__ __forceinline__ void split_cols(const GemmParams& p, int split, int64_t& c0, int64_t& c1) {
-  if (EPI == EPI_MAXTOK) {
+  if (EPI == EPI_MAXTOK && p.cu_seqlens == nullptr) {
     const int64_t s0 = int64_t(split) * p.segs_per_split;
     int64_t s1 = s0 + p.segs_per_split;
     if (s1 > p.n_segs) s1 = p.n_segs;
@@ -468,16 +476,41 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // EPI_MAXTOK per-row running state
       float run_max = BF16_LOWEST;
       float bias_v = 0.0f;
-      int64_t seg = 0, seg_end = 0;
+      int64_t seg = 0, seg_end = 0, seg_stop = 0, next_end = 0;
+      bool head_open = false;  // packed: the first document of the unit began in an earlier split (its piece goes to `edge`)
+      float head_piece = BF16_LOWEST;
       if (EPI == EPI_TOPK && tile_valid) {
         buf = p.cand + (int64_t(list_idx) * p.row_pad + row) * p.cap;
         if (row_valid && p.q_scale) qs = p.q_scale[row];
       }
       if (EPI == EPI_MAXTOK) {
         if (row_valid && p.bias) bias_v = p.bias[row];
-        seg = c0 / p.seg_len;
-        seg_end = c0 + p.seg_len;
+        if (p.cu_seqlens) {  // the end after next is fetched one document ahead of its use
+          seg = p.split_doc0[split];
+          head_open = int64_t(p.cu_seqlens[seg]) < c0;
+          seg_end = p.cu_seqlens[seg + 1];
+          next_end = p.cu_seqlens[min(seg + 2, p.n_segs)];
+        } else {
+          seg = int64_t(split) * p.segs_per_split;
+          seg_stop = min(seg + p.segs_per_split, p.n_segs);
+          seg_end = c0 + p.seg_len;
+        }
       }
+      // a document is complete: its activation goes to `out` — or, for the piece of a document that began earlier, the raw
+      // max is kept for the edge buffer
+      auto emit_doc = [&]() {
+        if (head_open) {
+          head_piece = run_max;
+          head_open = false;
+        } else {
+          float x = run_max;
+          if (p.relu) x = fmaxf(x, 0.0f);
+          if (p.log1p) x = log1pf(x);
+          if (row_valid) p.out[seg * p.rows + row] = x;
+        }
+        run_max = BF16_LOWEST;
+        ++seg;
+      };
       // The shared threshold and the column scales of a tile are fetched one tile ahead (a threshold that is one tile
       // stale is still a valid lower bound), so no global latency sits between two tiles of an epilogue-bound pass.
       uint32_t g_pref = 0;
@@ -628,20 +661,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             } else {  // EPI_MAXTOK
               const int64_t tok = cb + c * 32 + lane;
-              const bool mval = (tok < c1) && (p.mask[tok] != 0);
+              const bool mval = (tok < c1) && (p.mask == nullptr || p.mask[tok] != 0);
               const uint32_t mword = __ballot_sync(full, mval);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int64_t n = cb + c * 32 + j;
                 if (j < col_lim) {
-                  if (n == seg_end) {  // warp-uniform: a document ended right before this token
-                    float x = run_max;
-                    if (p.relu) x = fmaxf(x, 0.0f);
-                    if (p.log1p) x = log1pf(x);
-                    if (row_valid) p.out[seg * p.rows + row] = x;
-                    run_max = BF16_LOWEST;
-                    ++seg;
-                    seg_end += p.seg_len;
+                  while (n == seg_end) {  // warp-uniform: a document ended right before this token (empty ones: at once)
+                    emit_doc();
+                    if (p.cu_seqlens) {
+                      seg_end = next_end;
+                      next_end = p.cu_seqlens[min(seg + 2, p.n_segs)];
+                    } else {
+                      seg_end += p.seg_len;
+                    }
                   }
                   if ((mword >> j) & 1u) run_max = fmaxf(run_max, __uint_as_float(v[j]) + bias_v);
                 }
@@ -663,11 +696,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (EPI == EPI_TOPK && tile_valid) p.counts[int64_t(list_idx) * p.row_pad + row] = row_valid ? int32_t(cnt) : 0;
-      if (EPI == EPI_MAXTOK && c1 > c0) {
-        float x = run_max;
-        if (p.relu) x = fmaxf(x, 0.0f);
-        if (p.log1p) x = log1pf(x);
-        if (row_valid) p.out[seg * p.rows + row] = x;
+      if (EPI == EPI_MAXTOK && p.cu_seqlens == nullptr) {
+        // the document the split ends with
+        for (; seg < seg_stop;) emit_doc();
+      }
+      if (EPI == EPI_MAXTOK && p.cu_seqlens != nullptr && tile_valid) {
+        // documents that end exactly where the split ends (and empty ones there) are this unit's; one that goes on is a piece
+        while (seg < p.n_segs && seg_end <= c1) {
+          emit_doc();
+          seg_end = next_end;
+          next_end = p.cu_seqlens[min(seg + 2, p.n_segs)];
+        }
+        float tail_piece = BF16_LOWEST;
+        if (seg < p.n_segs) {  // the current document continues in the next split
+          if (head_open) head_piece = run_max;  // ... and began before this one: a single piece
+          else tail_piece = run_max;
+        }
+        if (row_valid) {
+          p.edge[(int64_t(split) * 2 + 0) * p.rows + row] = head_piece;
+          p.edge[(int64_t(split) * 2 + 1) * p.rows + row] = tail_piece;
+        }
       }
     });
   }

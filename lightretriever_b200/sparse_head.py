@@ -16,7 +16,9 @@ from typing import Optional
 import torch
 
 from . import _C
-from ._util import require_cuda, stream_ptr
+from ._util import Workspace, require_cuda, stream_ptr
+
+_WS = Workspace()
 
 
 def get_prompt_mask(input_ids: torch.Tensor, sep_token_id: int) -> torch.Tensor:
@@ -45,13 +47,61 @@ def get_sparse_attention_mask(input_ids: torch.Tensor, attention_mask: torch.Ten
     return mask
 
 
+def pack_tokens(hidden: torch.Tensor, mask: torch.Tensor, total: Optional[int] = None):
+    """hidden [B,S,d] bf16 + mask [B,S] -> (packed [T,d], cu_seqlens int32 [B+1], T): the valid tokens of every document,
+    concatenated.  ``total`` = number of valid tokens when the host already knows it (it owns the attention mask before
+    the backbone runs); otherwise one 4-byte device->host read."""
+    h = require_cuda(hidden, "hidden")
+    B, S, d = h.shape
+    m = require_cuda(mask, "mask").to(torch.uint8).contiguous()
+    cap = int(total) if total is not None else B * S
+    packed = torch.empty((max(cap, 1), d), dtype=torch.bfloat16, device=h.device)
+    cu = torch.empty(B + 1, dtype=torch.int32, device=h.device)
+    lib = _C.load()
+    with torch.cuda.device(h.device):
+        _C.check(lib.lr_pack_tokens(h.data_ptr(), m.data_ptr(), B, S, d, packed.data_ptr(), cap, cu.data_ptr(),
+                                    stream_ptr(h.device)))
+    T = int(total) if total is not None else int(cu[-1].item())
+    return packed[:max(T, 1)], cu, T
+
+
+def max_linear_mapping_packed(packed: torch.Tensor, cu_seqlens: torch.Tensor, total: int, weight_vd: torch.Tensor,
+                              bias: Optional[torch.Tensor] = None, relu: bool = False, log1p: bool = False) -> torch.Tensor:
+    """The same operator over packed tokens: ``packed`` [T, d] bf16 holds only valid tokens, document b = rows
+    ``cu_seqlens[b]:cu_seqlens[b+1]``; ``weight_vd`` = ``lm_head.weight`` [V, d].  No padding token is multiplied."""
+    h = require_cuda(packed, "packed")
+    W = require_cuda(weight_vd, "weight").to(torch.bfloat16).contiguous()
+    cu = require_cuda(cu_seqlens, "cu_seqlens").to(torch.int32).contiguous()
+    B = cu.numel() - 1
+    V, d = W.shape
+    if h.dtype != torch.bfloat16 or h.ndim != 2 or h.shape[1] != d or not h.is_contiguous():
+        raise ValueError("packed must be a contiguous [T, d] bfloat16 tensor")
+    b = None if bias is None else require_cuda(bias, "bias").to(torch.float32).contiguous()
+    out = torch.empty((B, V), dtype=torch.float32, device=h.device)
+    if total <= 0:  # no valid token at all: every document is the empty-document value (max_linear_map.py:27)
+        x = torch.full((B, V), float(torch.finfo(torch.bfloat16).min), dtype=torch.float32, device=h.device)
+        if relu:
+            x = torch.relu_(x)
+        return torch.log1p_(x) if log1p else x
+    lib = _C.load()
+    ws = _WS.get(lib.lr_sparse_head_packed_workspace_bytes(int(total), V), h.device)
+    with torch.cuda.device(h.device):
+        _C.check(lib.lr_sparse_head_max_packed(h.data_ptr(), W.data_ptr(), None if b is None else b.data_ptr(),
+                                               cu.data_ptr(), B, int(total), d, V, int(relu), int(log1p), out.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), stream_ptr(h.device)))
+    return out
+
+
 def max_linear_mapping(input: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
                        attention_mask: Optional[torch.Tensor] = None, relu: bool = False, log1p: bool = False,
-                       weight_is_vd: bool = False) -> torch.Tensor:
+                       weight_is_vd: bool = False, packed: Optional[bool] = None,
+                       valid_tokens: Optional[int] = None) -> torch.Tensor:
     """``max_t (input[b,t] @ weight + bias)`` over valid t -> [B, V] float32 (max_linear_map.py:175-188).
 
     weight is [d, V] as in the reference (``lm_head.weight.T``); pass ``weight_is_vd=True`` to hand over
-    ``lm_head.weight`` ([V, d]) directly and skip the transpose copy.
+    ``lm_head.weight`` ([V, d]) directly and skip the transpose copy.  With a mask the valid tokens are packed first
+    (``packed=None``: whenever a mask is given) so that padding is never multiplied; ``valid_tokens`` = ``mask.sum()``
+    when the host knows it already.  ``packed=False`` keeps the padded [B, S] layout (mask applied in the epilogue).
     """
     h = require_cuda(input, "input")
     if h.ndim != 3:
@@ -64,12 +114,17 @@ def max_linear_mapping(input: torch.Tensor, weight: torch.Tensor, bias: Optional
     V = Wvd.shape[0]
     h = h.to(torch.bfloat16).contiguous()
     Wvd = Wvd.to(torch.bfloat16).contiguous()
+    if attention_mask is not None and attention_mask.shape != (B, S):
+        raise ValueError("attention_mask must be [B, S]")
+    if packed is None:
+        packed = attention_mask is not None
+    if packed and attention_mask is not None:
+        hp, cu, T = pack_tokens(h, attention_mask, valid_tokens)
+        return max_linear_mapping_packed(hp, cu, T, Wvd, bias, relu=relu, log1p=log1p)
     if attention_mask is None:
         mask = torch.ones((B, S), dtype=torch.uint8, device=h.device)
     else:
         mask = require_cuda(attention_mask, "attention_mask").to(torch.uint8).contiguous()
-        if mask.shape != (B, S):
-            raise ValueError("attention_mask must be [B, S]")
     b = None if bias is None else require_cuda(bias, "bias").to(torch.float32).contiguous()
     out = torch.empty((B, V), dtype=torch.float32, device=h.device)
     lib = _C.load()
@@ -118,11 +173,12 @@ def sparsify_quantize(reps: torch.Tensor, top_k: int = 0, min_tokens_to_keep: in
 def sparse_head(hidden_states: torch.Tensor, lm_head_weight: torch.Tensor, bias: Optional[torch.Tensor],
                 sparse_attention_mask: torch.Tensor, sparse_use_relu: bool = True,
                 sparse_use_log_saturation: bool = True, sparse_top_k: int = 0, sparse_min_tokens_to_keep: int = 8,
-                quantization_factor: float = 100.0):
-    """hidden [B,S,d] -> CSR of integer impacts: aggregate + get_sparse_emb + convert_sparse_reps_to_json in two
-    device passes (GEMM with max/relu/log1p epilogue, then select/quantise)."""
+                quantization_factor: float = 100.0, valid_tokens: Optional[int] = None):
+    """hidden [B,S,d] -> CSR of integer impacts: aggregate + get_sparse_emb + convert_sparse_reps_to_json on the device:
+    pack the valid tokens, GEMM with max/relu/log1p epilogue over the packed tokens, select/quantise.
+    ``valid_tokens`` = ``sparse_attention_mask.sum()`` when the host knows it (saves a 4-byte read-back)."""
     reps = max_linear_mapping(hidden_states, lm_head_weight, bias, sparse_attention_mask, relu=sparse_use_relu,
-                              log1p=sparse_use_log_saturation, weight_is_vd=True)
+                              log1p=sparse_use_log_saturation, weight_is_vd=True, valid_tokens=valid_tokens)
     return sparsify_quantize(reps, sparse_top_k, sparse_min_tokens_to_keep, quantization_factor)
 
 

@@ -298,8 +298,9 @@ def test_sparse_head_golden(golden_dir):
     np.testing.assert_allclose(got_rl, np.log1p(np.maximum(ref, 0)), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("packed", [True, False])
 @pytest.mark.parametrize("B,S,d,V", [(3, 64, 128, 1000), (5, 100, 256, 3001), (2, 512, 512, 5000), (9, 33, 64, 129)])
-def test_sparse_head_vs_oracle(B, S, d, V):
+def test_sparse_head_vs_oracle(B, S, d, V, packed):
     gen = torch.Generator().manual_seed(S)
     h = torch.randn(B, S, d, generator=gen).bfloat16()
     W = (torch.randn(V, d, generator=gen) * 0.05).bfloat16()
@@ -310,7 +311,7 @@ def test_sparse_head_vs_oracle(B, S, d, V):
     am[1, :2] = 1  # nothing valid once first/last are dropped
     mask = oracle.sparse_attention_mask(torch.zeros(B, S, dtype=torch.long), am, sep_token_id=-1)
     ref = oracle.max_linear_map(h.float(), W.float().T, bias, mask)
-    got = lr.max_linear_mapping(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), weight_is_vd=True).cpu()
+    got = lr.max_linear_mapping(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), weight_is_vd=True, packed=packed).cpu()
     fin = ref > -1e30
     torch.testing.assert_close(got[fin], ref[fin], rtol=1e-4, atol=1e-4)
     assert bool((got[~fin] < -1e30).all())
@@ -329,6 +330,46 @@ def test_sparse_head_vs_oracle(B, S, d, V):
         assert len(common) >= 0.9 * len(ej)
         for t in common:
             assert abs(gj[t] - ej[t]) <= max(1, 0.01 * ej[t])
+
+
+@pytest.mark.parametrize("tiles_per_split", [None, 1, 3, 1000])
+def test_sparse_head_packed_ragged_documents(monkeypatch, tiles_per_split):
+    """Packed tokens (lr_pack_tokens + lr_sparse_head_max_packed): ragged lengths from 0 to S, empty documents at the
+    start, in the middle and at the end, masked tokens inside a document, and splits cut at whole 256-token tiles — with
+    one tile per split a 700-token document crosses two cuts and covers a whole split, others end exactly on a cut.
+    Bit-identical to the padded kernel (same products, same max), and both match the oracle."""
+    B, S, d, V = 37, 700, 128, 2500
+    gen = torch.Generator().manual_seed(11)
+    h = torch.randn(B, S, d, generator=gen).bfloat16()
+    W = (torch.randn(V, d, generator=gen) * 0.05).bfloat16()
+    bias = torch.randn(V, generator=gen) * 0.1
+    lens = torch.randint(0, 301, (B,), generator=gen)
+    lens[[0, 1, 7, 8, 20, B - 1]] = 0
+    lens[5] = S
+    lens[2] = 256 - int(lens[:2].sum())          # documents 0..2 end exactly on the first tile boundary
+    lens[3] = 256
+    mask = torch.arange(S)[None] < lens[:, None]
+    holes = torch.rand(B, S, generator=gen) > 0.1  # holes inside the documents (not in the two that pin the boundary)
+    holes[2:4] = True
+    mask &= holes
+    if tiles_per_split is not None:
+        monkeypatch.setenv("LR_SPARSE_HEAD_TILES_PER_SPLIT", str(tiles_per_split))
+    hp, cu, T = lr.pack_tokens(h.cuda(), mask.cuda())
+    assert T == int(mask.sum()) and cu.cpu().tolist() == [0] + torch.cumsum(mask.sum(1), 0).tolist()
+    assert torch.equal(hp.cpu(), h[mask])
+    got = lr.max_linear_mapping(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), weight_is_vd=True, valid_tokens=T).cpu()
+    pad = lr.max_linear_mapping(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), weight_is_vd=True, packed=False).cpu()
+    assert torch.equal(got, pad)
+    ref = oracle.max_linear_map(h.float(), W.float().T, bias, mask)
+    fin = ref > -1e30
+    torch.testing.assert_close(got[fin], ref[fin], rtol=1e-4, atol=1e-4)
+    assert bool((got[~fin] < -1e30).all()) and int((~fin).any(1).sum()) >= 6
+    act = lr.max_linear_mapping(h.cuda(), W.cuda(), bias.cuda(), mask.cuda(), relu=True, log1p=True, weight_is_vd=True).cpu()
+    torch.testing.assert_close(act, torch.log1p(torch.relu(ref)), rtol=1e-4, atol=1e-5)
+    # nothing valid at all
+    none = lr.max_linear_mapping(h.cuda(), W.cuda(), None, torch.zeros(B, S, dtype=torch.bool).cuda(), relu=True, log1p=True,
+                                 weight_is_vd=True)
+    assert float(none.abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("window", [1, 3])
