@@ -660,23 +660,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   if (j < col_lim) p.dbg_scores[row * p.cols + cb + c * 32 + j] = __uint_as_float(v[j]);
               }
             } else {  // EPI_MAXTOK
-              const int64_t tok = cb + c * 32 + lane;
+              const int64_t base = cb + c * 32;
+              const int64_t tok = base + lane;
               const bool mval = (tok < c1) && (p.mask == nullptr || p.mask[tok] != 0);
-              const uint32_t mword = __ballot_sync(full, mval);
+              uint32_t m = __ballot_sync(full, mval);  // valid tokens of the chunk still to be folded
+              const int ncols = col_lim < 32 ? col_lim : 32;
+              // Usually no document ends inside the chunk: one pass over its 32 columns.  When one does, the columns before
+              // the end are folded, the document is emitted, and the pass repeats over the rest (the loop body exists once:
+              // the kernel's instruction footprint matters more than the second pass).
+#pragma unroll 1
+              for (;;) {
+                const int64_t lim = seg_end - base;  // columns of the chunk that belong to the current document
+                const bool ends_here = lim < int64_t(ncols);  // warp-uniform
+                const uint32_t part = ends_here ? (m & ((1u << int(lim)) - 1u)) : m;
+                if (part) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t n = cb + c * 32 + j;
-                if (j < col_lim) {
-                  while (n == seg_end) {  // warp-uniform: a document ended right before this token (empty ones: at once)
-                    emit_doc();
-                    if (p.cu_seqlens) {
-                      seg_end = next_end;
-                      next_end = p.cu_seqlens[min(seg + 2, p.n_segs)];
-                    } else {
-                      seg_end += p.seg_len;
-                    }
-                  }
-                  if ((mword >> j) & 1u) run_max = fmaxf(run_max, __uint_as_float(v[j]) + bias_v);
+                  for (int j = 0; j < 32; ++j)
+                    if ((part >> j) & 1u) run_max = fmaxf(run_max, __uint_as_float(v[j]) + bias_v);
+                }
+                if (!ends_here) break;
+                m &= ~part;
+                emit_doc();
+                if (p.cu_seqlens) {
+                  seg_end = next_end;
+                  next_end = p.cu_seqlens[min(seg + 2, p.n_segs)];
+                } else {
+                  seg_end += p.seg_len;
                 }
               }
             }
