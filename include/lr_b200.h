@@ -216,6 +216,13 @@ int lr_sparse_head_max_packed(const void* hidden, const void* W, const float* bi
 int lr_pack_tokens(const void* hidden, const uint8_t* mask, int64_t B, int64_t S, int64_t d, void* packed,
                    int64_t cap, int32_t* cu_seqlens, void* stream);
 
+/* top_p_sampling (finetune/sparse_pooling.py:64-87, called at modeling_hybrid.py:189-195 with sparse_top_p_qry/_psg):
+ * in ascending order of value, entries are set to 0 while the cumulative softmax probability up to and including them
+ * is <= 1 - top_p; the min_keep largest always stay; top_p outside (0, 1) is a no-op.  reps [B, V] f32, in place.
+ * The reference's float32 cumsum has no defined rounding: entries whose cumulative probability is within ~1e-6 of the
+ * bound may differ (tests state the band). */
+int lr_top_p_filter(float* reps, int64_t B, int64_t V, float top_p, int min_keep, void* stream);
+
 /* top_k_sampling (finetune/sparse_pooling.py:89-106: keep every entry >= the k_eff-th
  * largest, k_eff = min(max(top_k, min_keep), V), top_k <= 0 disables) followed by the
  * quantiser of convert_sparse_reps_to_json_pt (finetune/sparse_converter_mixin.py:103-160):

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "lr_sparse_head_max": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "lr_sparse_head_packed_workspace_bytes": (_sz, [_i64, _i64]),
     "lr_sparse_head_max_packed": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "lr_top_p_filter": (_i32, [_vp, _i64, _i64, _f32, _i32, _vp]),
     "lr_pack_tokens": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "lr_sparsify_scratch_bytes": (_sz, [_i64, _i64]),
     "lr_sparsify_quantize": (_i32, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -10,7 +10,8 @@ from .search import (FlatIPIndex, FlatIPSearch, decode_keys, drop_identical, enc
                      flatip_topk_sharded, merge_keys, topk_merge)
 from .sharded import ShardedFlatIPIndex, ShardedImpactIndex, exchange_candidates, shard_range
 from .sparse_head import (aggregate, convert_sparse_reps_to_json, csr_to_json, get_sparse_attention_mask,
-                          max_linear_mapping, max_linear_mapping_packed, pack_tokens, sparse_head, sparsify_quantize)
+                          max_linear_mapping, max_linear_mapping_packed, pack_tokens, sparse_head, sparsify_quantize,
+                          top_p_sampling)
 from .sparse_search import ImpactIndex, ImpactSearch
 from .online import OnlineSearcher
 from .hybrid import HybridSearch, fuse_scores_linear, fuse_scores_rrf, fuse_topk_device

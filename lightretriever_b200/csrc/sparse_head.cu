@@ -160,6 +160,156 @@ sparsify_write_kernel(const float* __restrict__ reps, int64_t V, float quant, co
   }
 }
 
+// ---- top_p_sampling (finetune/sparse_pooling.py:64-87): ascending sort, softmax, cumulative sum; an entry is zeroed while
+// the cumulative probability up to and including it is <= 1 - top_p, and the last min_keep entries of the sorted order
+// (the largest) always stay.  Here without a sort: an 8-bit radix descent over the order-preserving keys finds the
+// value at which the cumulative mass crosses 1 - top_p (masses as 2^-44 fixed point in u64, so the sums do not depend on
+// the order of the atomics); entries below it go, and of the entries equal to it the first few by index (a stable
+// sort's order).  One CTA per document; in place.
+constexpr int TP_THREADS = 512;
+constexpr double TP_SCALE = 17592186044416.0;  // 2^44
+
+__device__ __forceinline__ float tp_block_max(float v, float* red) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, off));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < TP_THREADS / 32; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(TP_THREADS)
+top_p_filter_kernel(float* __restrict__ reps, int64_t V, float top_p, int min_keep) {
+  __shared__ unsigned long long mass[256];
+  __shared__ uint32_t cnt[256];
+  __shared__ float red[TP_THREADS / 32];
+  __shared__ double red_d[TP_THREADS / 32];
+  __shared__ uint32_t s_bin, s_below_cnt, s_eq;
+  __shared__ unsigned long long s_below_mass;
+  __shared__ uint32_t s_tie_seen;
+  float* x = reps + int64_t(blockIdx.x) * V;
+  const int tid = threadIdx.x;
+  // softmax denominator (double: the reference accumulates 1e5 float terms; no order of ours reproduces its rounding)
+  float mx = -INFINITY;
+  for (int64_t i = tid; i < V; i += TP_THREADS) mx = fmaxf(mx, x[i]);
+  mx = tp_block_max(mx, red);
+  double z = 0.0;
+  for (int64_t i = tid; i < V; i += TP_THREADS) z += double(expf(x[i] - mx));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) z += __shfl_xor_sync(0xFFFFFFFFu, z, off);
+  if ((tid & 31) == 0) red_d[tid >> 5] = z;
+  __syncthreads();
+  z = 0.0;
+  for (int i = 0; i < TP_THREADS / 32; ++i) z += red_d[i];
+  const double inv_z = TP_SCALE / z;
+  auto mass_of = [&](float v) { return static_cast<unsigned long long>(double(expf(v - mx)) * inv_z + 0.5); };
+  // cumulative mass that may be removed; the count cap keeps the min_keep largest
+  const unsigned long long target = static_cast<unsigned long long>((1.0 - double(top_p)) * TP_SCALE);
+  const uint32_t max_remove = V > min_keep ? uint32_t(V - min_keep) : 0u;
+  // ---- descent 1: by mass.  prefix = key bits fixed so far; below = (mass, count) of all keys smaller than the prefix range
+  uint32_t prefix = 0;
+  unsigned long long below_mass = 0;
+  uint32_t below_cnt = 0;
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    if (tid < 256) {
+      mass[tid] = 0;
+      cnt[tid] = 0;
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < V; i += TP_THREADS) {
+      const uint32_t k = f32_to_key(x[i]);
+      if (pass == 3 || (k >> (shift + 8)) == prefix) {
+        atomicAdd(&mass[(k >> shift) & 0xFFu], mass_of(x[i]));
+        atomicAdd(&cnt[(k >> shift) & 0xFFu], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {  // ascending walk: the first bin whose cumulative mass exceeds the target holds the crossing value
+      unsigned long long m = below_mass;
+      uint32_t c = below_cnt;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (m + mass[b] > target) break;
+        m += mass[b];
+        c += cnt[b];
+      }
+      s_bin = uint32_t(b);
+      s_below_mass = m;
+      s_below_cnt = c;
+      s_eq = cnt[b];  // after the last pass: the number of entries equal to the crossing value
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | s_bin;
+    below_mass = s_below_mass;
+    below_cnt = s_below_cnt;
+    __syncthreads();
+  }
+  // entries with a smaller key go; of the s_eq entries equal to it, the first `ties` by index
+  uint32_t vkey = prefix;
+  uint32_t ties;
+  {
+    const unsigned long long mv = mass_of(key_to_f32(vkey));
+    // zero-mass entries never move the sum: all of them are at or below the bound
+    const unsigned long long t = mv == 0 ? 0xFFFFFFFFull : (target >= below_mass ? (target - below_mass) / mv : 0ull);
+    ties = t > s_eq ? s_eq : uint32_t(t);
+  }
+  if (below_cnt + ties > max_remove) {
+    // ---- descent 2: the min_keep cap binds: remove exactly the max_remove smallest, i.e. cut at that rank's value
+    uint32_t pre2 = 0, below2 = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      if (tid < 256) cnt[tid] = 0;
+      __syncthreads();
+      for (int64_t i = tid; i < V; i += TP_THREADS) {
+        const uint32_t k = f32_to_key(x[i]);
+        if (pass == 3 || (k >> (shift + 8)) == pre2) atomicAdd(&cnt[(k >> shift) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t c = below2;
+        int b = 0;
+        for (; b < 255; ++b) {
+          if (c + cnt[b] > max_remove) break;
+          c += cnt[b];
+        }
+        s_bin = uint32_t(b);
+        s_below_cnt = c;
+      }
+      __syncthreads();
+      pre2 = (pre2 << 8) | s_bin;
+      below2 = s_below_cnt;
+      __syncthreads();
+    }
+    vkey = pre2;
+    ties = max_remove - below2;
+  }
+  // ---- apply: ties are taken in index order (chunks of the block, ballot scan inside a chunk)
+  if (tid == 0) s_tie_seen = 0;
+  __syncthreads();
+  __shared__ uint32_t warp_eq[TP_THREADS / 32];
+  for (int64_t i0 = 0; i0 < V; i0 += TP_THREADS) {
+    const int64_t i = i0 + tid;
+    const uint32_t k = i < V ? f32_to_key(x[i]) : 0xFFFFFFFFu;
+    const bool eq = i < V && k == vkey;
+    const uint32_t em = __ballot_sync(0xFFFFFFFFu, eq);
+    if ((tid & 31) == 0) warp_eq[tid >> 5] = __popc(em);
+    __syncthreads();
+    uint32_t before = s_tie_seen, total = 0;
+    for (int w = 0; w < TP_THREADS / 32; ++w) {
+      if (w < (tid >> 5)) before += warp_eq[w];
+      total += warp_eq[w];
+    }
+    const uint32_t rank = before + __popc(em & ((1u << (tid & 31)) - 1u));
+    if (i < V && (k < vkey || (eq && rank < ties))) x[i] = 0.0f;
+    __syncthreads();
+    if (tid == 0) s_tie_seen += total;
+    __syncthreads();
+  }
+}
+
 // ---- packed tokens: documents that cross a split boundary
 // tiles [t0, t1) of split s (the same balanced ranges as umma_gemm.cuh split_cols)
 __device__ __forceinline__ void packed_split_range(int split, int splits, int64_t n_tiles, int64_t T, int64_t& c0, int64_t& c1) {
@@ -435,6 +585,16 @@ extern "C" int lr_pack_tokens(const void* hidden, const uint8_t* mask, int64_t B
   if (rc) return rc;
   pack_rows_kernel<<<dim3(unsigned(B), PACK_SLICES), 256, size_t(S) * 4, st>>>(
       static_cast<const uint8_t*>(hidden), mask, S, d * 2, cu_seqlens, static_cast<uint8_t*>(packed), cap);
+  LR_LAUNCH_CHECK();
+  return LR_OK;
+}
+
+extern "C" int lr_top_p_filter(float* reps, int64_t B, int64_t V, float top_p, int min_keep, void* stream) {
+  LR_CHECK_ARG(reps, "top_p_filter: null pointer");
+  LR_CHECK_ARG(B >= 1 && V >= 1 && V < (int64_t(1) << 31), "top_p_filter: bad sizes");
+  if (!(top_p > 0.0f && top_p < 1.0f)) return LR_OK;  // sparse_pooling.py:73-74: outside (0, 1) the filter is off
+  if (min_keep < 0) min_keep = 0;
+  top_p_filter_kernel<<<unsigned(B), TP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(reps, V, top_p, min_keep);
   LR_LAUNCH_CHECK();
   return LR_OK;
 }

@@ -144,6 +144,26 @@ def aggregate(hidden_states: torch.Tensor, lm_head, sparse_attention_mask: torch
                               weight_is_vd=True)
 
 
+def top_p_sampling(scores: torch.Tensor, top_p: float, filter_value: float = 0.0, min_tokens_to_keep: int = 1,
+                   inplace: bool = False) -> torch.Tensor:
+    """``top_p_sampling`` (sparse_pooling.py:64-87) on device: entries whose cumulative softmax probability, taken in
+    ascending order, stays <= 1 - top_p are set to 0; the ``min_tokens_to_keep`` largest always stay.  Returns a new
+    tensor like the reference unless ``inplace``.  Only the reference's ``filter_value = 0`` is built."""
+    if top_p <= 0 or top_p >= 1:
+        return scores
+    if filter_value != 0.0:
+        raise NotImplementedError("top_p_sampling: the reference only ever filters to 0")
+    x = require_cuda(scores, "scores")
+    if x.dtype != torch.float32 or not x.is_contiguous() or not inplace:
+        x = x.to(torch.float32).contiguous().clone() if not inplace else x.to(torch.float32).contiguous()
+    x2 = x.view(-1, x.shape[-1])
+    lib = _C.load()
+    with torch.cuda.device(x.device):
+        _C.check(lib.lr_top_p_filter(x2.data_ptr(), x2.shape[0], x2.shape[1], float(top_p), int(min_tokens_to_keep),
+                                     stream_ptr(x.device)))
+    return x
+
+
 def sparsify_quantize(reps: torch.Tensor, top_k: int = 0, min_tokens_to_keep: int = 8, quantization_factor: float = 100.0,
                       cap: Optional[int] = None):
     """top_k_sampling + clamp/round quantiser -> CSR (indptr int32 [B+1], token ids int32, impacts uint16)."""
@@ -173,12 +193,14 @@ def sparsify_quantize(reps: torch.Tensor, top_k: int = 0, min_tokens_to_keep: in
 def sparse_head(hidden_states: torch.Tensor, lm_head_weight: torch.Tensor, bias: Optional[torch.Tensor],
                 sparse_attention_mask: torch.Tensor, sparse_use_relu: bool = True,
                 sparse_use_log_saturation: bool = True, sparse_top_k: int = 0, sparse_min_tokens_to_keep: int = 8,
-                quantization_factor: float = 100.0, valid_tokens: Optional[int] = None):
+                quantization_factor: float = 100.0, valid_tokens: Optional[int] = None, sparse_top_p: float = 1.0):
     """hidden [B,S,d] -> CSR of integer impacts: aggregate + get_sparse_emb + convert_sparse_reps_to_json on the device:
-    pack the valid tokens, GEMM with max/relu/log1p epilogue over the packed tokens, select/quantise.
+    pack the valid tokens, GEMM with max/relu/log1p epilogue over the packed tokens, (top-p,) select/quantise
+    (modeling_hybrid.py:183-201 order: relu, log1p, top-p, top-k).
     ``valid_tokens`` = ``sparse_attention_mask.sum()`` when the host knows it (saves a 4-byte read-back)."""
     reps = max_linear_mapping(hidden_states, lm_head_weight, bias, sparse_attention_mask, relu=sparse_use_relu,
                               log1p=sparse_use_log_saturation, weight_is_vd=True, valid_tokens=valid_tokens)
+    reps = top_p_sampling(reps, sparse_top_p, min_tokens_to_keep=sparse_min_tokens_to_keep, inplace=True)
     return sparsify_quantize(reps, sparse_top_k, sparse_min_tokens_to_keep, quantization_factor)
 
 

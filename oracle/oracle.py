@@ -13,6 +13,7 @@ tests/golden/*.npz by importing the reference itself in the build container):
   sparse_attention_mask PINNED   vs lightretriever.finetune.sparse_pooling.get_sparse_attention_mask (imported)
   max_linear_map        PINNED   vs lightretriever.utils.max_linear_map.max_linear_mapping (imported)
   top_k_sampling        PINNED   vs lightretriever.finetune.sparse_pooling.top_k_sampling (imported)
+  top_p_sampling        PINNED   vs lightretriever.finetune.sparse_pooling.top_p_sampling (imported; gen_golden_r2.py)
   quantize_reps         PINNED   vs SparseConverterMixin.convert_sparse_reps_to_json_pt (imported with the missing Rust
                                  wheel stubbed); the Rust converter itself is absent -> its rounding is PARITY UNPINNED
   fuse_linear/fuse_rrf  PINNED   vs lightretriever.retriever.score_fuse_utils (imported)
@@ -20,9 +21,11 @@ tests/golden/*.npz by importing the reference itself in the build container):
   flatten_token_ids     PINNED   vs tokenize_nonctx_qry_emb_bag when the module imports, else restated (see gen_golden)
   flatip_topk           PARITY UNPINNED: faiss (>=1.7.4, no lock file) is not installed and the reference holds no golden
                                  vectors for it; restated from its call sites (retriever/faiss_index.py:27-40) and anchored
-                                 on the score definition torch.matmul(q, p.T) (finetune/modeling_encoder.py:414-427)
-  impact_topk           PARITY UNPINNED: io.anserini:anserini:0.25.0 (JVM) is absent; restated from the reference's own
-                                 formula compute_similarity (scripts/asymmetric_sparse_infer.ipynb:207-228), int64 math
+                                 on the score definition torch.matmul(q, p.T) (finetune/modeling_encoder.py:414-427); the
+                                 score line of scripts/asymmetric_dense_infer.ipynb:231 is exec'd by gen_golden_r2.py
+  impact_topk           io.anserini:anserini:0.25.0 (JVM) is absent, so Lucene's tie order stays PARITY UNPINNED; the SCORE
+                                 definition is PINNED: impact_scores equals the notebook's own compute_similarity cell
+                                 (scripts/asymmetric_sparse_infer.ipynb:207-228), exec'd by gen_golden_r2.py
 """
 from __future__ import annotations
 
@@ -91,6 +94,12 @@ def sort_desc_id_asc(scores: np.ndarray, ids: np.ndarray, k: int):
     return scores[order], ids[order]
 
 
+def flatip_scores(q, corpus) -> torch.Tensor:
+    """The score definition of the dense path: scripts/asymmetric_dense_infer.ipynb:231
+    (`scores = query_embeddings @ corpus_embedding.T`), finetune/modeling_encoder.py:414-427; fp32."""
+    return torch.as_tensor(q).float() @ torch.as_tensor(corpus).float().T
+
+
 def flatip_topk(q, corpus, k: int, id_offset: int = 0, chunk: int = 65536):
     """retriever/faiss_index.py:27-40: IndexFlatIP.search(q, k) -> (scores f32 [Q,k] descending, ids i64 [Q,k]).
 
@@ -102,7 +111,7 @@ def flatip_topk(q, corpus, k: int, id_offset: int = 0, chunk: int = 65536):
     best_s = np.full((Q, 0), -np.inf, dtype=np.float32)
     best_i = np.full((Q, 0), -1, dtype=np.int64)
     for lo in range(0, N, chunk):
-        s = (q @ corpus[lo:lo + chunk].T).numpy()
+        s = flatip_scores(q, corpus[lo:lo + chunk]).numpy()
         i = np.broadcast_to(np.arange(lo, lo + s.shape[1], dtype=np.int64), s.shape)
         cs = np.concatenate([best_s, s], axis=1)
         ci = np.concatenate([best_i, i], axis=1)
@@ -242,13 +251,30 @@ def top_k_sampling(scores: torch.Tensor, top_k: int, filter_value: float = 0.0, 
     return scores.masked_fill(remove, filter_value)
 
 
-def get_sparse_emb(logits, relu: bool = True, log1p: bool = True, top_k: int = 0, min_tokens_to_keep: int = 8):
-    """finetune/modeling_hybrid.py:183-201 (top-p at its default 1.0 is a no-op, sparse_pooling.py:73-74)."""
+def top_p_sampling(scores: torch.Tensor, top_p: float, filter_value: float = 0.0, min_tokens_to_keep: int = 1):
+    """finetune/sparse_pooling.py:64-87: ascending sort, softmax, cumsum; remove while cumulative <= 1 - top_p, never the
+    last min_tokens_to_keep of the sorted order.  Returns (filtered scores, cumulative probability of every entry in
+    the original indexing) — the second value lets a test state which entries sit on the bound."""
+    if top_p <= 0 or top_p >= 1:
+        return scores, None
+    sorted_logits, sorted_indices = torch.sort(scores, descending=False, stable=True)
+    cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+    remove_sorted = cum <= (1 - top_p)
+    remove_sorted[..., -min_tokens_to_keep:] = False
+    remove = remove_sorted.scatter(1, sorted_indices, remove_sorted)
+    cum_orig = torch.empty_like(cum).scatter(1, sorted_indices, cum)
+    return scores.masked_fill(remove, filter_value), cum_orig
+
+
+def get_sparse_emb(logits, relu: bool = True, log1p: bool = True, top_k: int = 0, min_tokens_to_keep: int = 8,
+                   top_p: float = 1.0):
+    """finetune/modeling_hybrid.py:183-201: relu, log1p, top-p (its default 1.0 is a no-op, sparse_pooling.py:73-74), top-k."""
     x = torch.as_tensor(logits).float().clone()
     if relu:
         x = torch.relu(x)
     if log1p:
         x = torch.log1p(x)
+    x = top_p_sampling(x, top_p, min_tokens_to_keep=min_tokens_to_keep)[0]
     return top_k_sampling(x, top_k, min_tokens_to_keep=min_tokens_to_keep)
 
 

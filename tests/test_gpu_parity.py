@@ -396,6 +396,51 @@ def test_sparse_head_team_schedule_matches_round_robin(monkeypatch, window):
     torch.testing.assert_close(rr.cpu(), ref, rtol=1e-4, atol=1e-4)
 
 
+def test_top_p_sampling_golden(golden_dir):
+    """lr_top_p_filter vs the imported reference's outputs (tests/golden/top_p.npz).  The reference's float32 cumsum has
+    no defined rounding, so an entry may differ only when its cumulative probability lies within 2e-6 of the bound
+    1 - top_p (the oracle returns that probability); the entries kept by the min_keep rule must agree exactly."""
+    g = np.load(os.path.join(golden_dir, "top_p.npz"))
+    reps = torch.from_numpy(g["reps"])
+    for name in (k for k in g.files if k != "reps"):
+        tp, mk = float(name.split("_")[0][1:]), int(name.split("_k")[1])
+        got = _np(lr.top_p_sampling(reps.cuda(), tp, min_tokens_to_keep=mk))
+        ref = g[name]
+        if tp <= 0 or tp >= 1:
+            np.testing.assert_array_equal(got, ref)
+            continue
+        _, cum = oracle.top_p_sampling(reps.clone(), tp, min_tokens_to_keep=mk)
+        diff = got != ref
+        near = np.abs(cum.numpy() - (1.0 - tp)) <= 2e-6
+        assert not (diff & ~near).any(), (name, int(diff.sum()), int((diff & ~near).sum()))
+        assert diff.sum() <= 2 * reps.shape[0], (name, int(diff.sum()))
+        assert ((got == 0) | (got == g["reps"])).all()
+        # the rows where the min_keep cap binds keep exactly the min_keep largest entries
+        for r in range(reps.shape[0]):
+            if (ref[r] != 0).sum() == mk and (g["reps"][r] != 0).sum() > mk:
+                np.testing.assert_array_equal(got[r], ref[r])
+    x = reps.cuda().clone()
+    assert lr.top_p_sampling(x, 0.3, min_tokens_to_keep=8, inplace=True).data_ptr() == x.data_ptr()
+
+
+def test_score_definitions_match_the_reference_notebook_cells_on_device(golden_dir):
+    """K4 and K2 against the reference's own notebook cells (exec'd by oracle/gen_golden_r2.py): integer impact scores
+    bit-exact, dense scores within 1e-2 relative (bf16 inputs vs the notebook's fp32)."""
+    g = np.load(os.path.join(golden_dir, "notebook_cells.npz"))
+    queries = [{int(k): v for k, v in q.items()} for q in json.loads(str(g["sparse_queries"]))]
+    docs = json.loads(str(g["sparse_docs"]))
+    s = lr.ImpactSearch(vocab_size=400)
+    s.index(docs, [str(j) for j in range(len(docs))])
+    res = s.retrieve_with_emb(queries, [f"q{i}" for i in range(len(queries))], top_k=len(docs))
+    ref = g["sparse_scores"]
+    for qi in range(len(queries)):
+        exp = {str(j): float(ref[qi, j]) for j in range(len(docs)) if ref[qi, j] > 0}
+        assert res.get(f"q{qi}", {}) == exp
+    q, c = torch.from_numpy(g["dense_q"]).cuda(), torch.from_numpy(g["dense_c"]).cuda()
+    got = _np(lr.flatip_scores(q.bfloat16(), c.bfloat16()))
+    np.testing.assert_allclose(got, g["dense_scores"], rtol=1e-2, atol=1e-2 * np.abs(g["dense_scores"]).max())
+
+
 def test_quantiser_golden_bit_exact(golden_dir):
     g = np.load(os.path.join(golden_dir, "quantize.npz"))
     got = lr.convert_sparse_reps_to_json(torch.from_numpy(g["reps"]).cuda(), quantization_factor=100)

@@ -69,6 +69,33 @@ def test_topk_sampling_matches_reference(golden_dir):
     np.testing.assert_array_equal(oracle.get_sparse_emb(g["out_f32"], True, True, 20, 8).numpy(), g["topk20"])
 
 
+def test_top_p_sampling_matches_reference(golden_dir):
+    """oracle.top_p_sampling vs the imported sparse_pooling.top_p_sampling (oracle/gen_golden_r2.py), bit for bit."""
+    g = _load(golden_dir, "top_p.npz")
+    reps = torch.from_numpy(g["reps"])
+    cases = [k for k in g.files if k != "reps"]
+    assert len(cases) >= 8
+    for k in cases:
+        tp, mk = float(k.split("_")[0][1:]), int(k.split("_k")[1])
+        np.testing.assert_array_equal(oracle.top_p_sampling(reps.clone(), tp, min_tokens_to_keep=mk)[0].numpy(), g[k])
+
+
+def test_score_definitions_match_the_reference_notebook_cells(golden_dir):
+    """The K4 and K2 score definitions are the reference's own notebook cells, exec'd by oracle/gen_golden_r2.py:
+    compute_similarity (asymmetric_sparse_infer.ipynb:207-228) and `query_embeddings @ corpus_embedding.T`
+    (asymmetric_dense_infer.ipynb:231)."""
+    g = _load(golden_dir, "notebook_cells.npz")
+    queries = [{int(k): v for k, v in q.items()} for q in json.loads(str(g["sparse_queries"]))]
+    docs = [{int(k): v for k, v in d.items()} for d in json.loads(str(g["sparse_docs"]))]
+    np.testing.assert_array_equal(oracle.impact_scores(queries, docs), g["sparse_scores"])
+    s, i = oracle.impact_topk(queries, docs, 10)
+    for r in range(len(queries)):
+        hit = i[r] >= 0
+        np.testing.assert_array_equal(s[r][hit], g["sparse_scores"][r][i[r][hit]].astype(np.float32))
+    dense = oracle.flatip_scores(torch.from_numpy(g["dense_q"]), torch.from_numpy(g["dense_c"])).numpy()
+    np.testing.assert_array_equal(dense, g["dense_scores"])
+
+
 def test_quantiser_matches_reference_torch_twin(golden_dir):
     g = _load(golden_dir, "quantize.npz")
     assert oracle.quantize_reps(g["reps"], 100) == json.loads(str(g["json"]))
