@@ -221,9 +221,9 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
   // of a single main pass take k*N/prefix = 3.4k candidates per query; ranges growing 4x per pass bring that below 1k.
   int main_begin = prefix_tiles;
   pl.n_mid = 0;
-  const int refresh = env.refresh >= 0 ? env.refresh : (d_used <= 1024 ? 1 : 0);
-  if (refresh && pt_global >= 128 && prefix_tiles > 0 && prefix_splits_forced == 0 &&
-      pt_global == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN)) {
+  // (a forced prefix size, LR_FLATIP_PREFIX_DOCS, refreshes only when LR_FLATIP_REFRESH asks for it: tests pin the plan)
+  const int refresh = env.refresh >= 0 ? env.refresh : ((d_used <= 1024 && want < 0) ? 1 : 0);
+  if (refresh && pt_global >= 128 && prefix_tiles > 0 && prefix_splits_forced == 0) {
     int growth = env.refresh_growth;
     if (growth < 2) growth = 2;
     // ranges end at growth^i times the WHOLE prefix (a shard's thresholds start from the exchanged k-th best of it)

@@ -567,6 +567,39 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // funnel shift per score, in four independent 8-score chains — the epilogue warp is alone on its scheduler, so
           // dependent chains, not issue slots, set its pace.
           auto pass_mask = [&](const uint32_t (&v)[32], int c) -> uint32_t {
+            const int lim = n_valid - c * 32;  // columns >= lim are padding
+            // Fast reject: with warm thresholds almost no chunk holds a passing score, and whether one does costs half the
+            // instructions of locating it — the largest score of the chunk (3-input max tree), or with column scales the
+            // smallest thr_s - v * cs (the same FFMA as the mask below, so the two can never disagree), then one vote.
+            if (lim >= 32) {  // warp-uniform
+              bool hit;
+              if (has_scale) {
+                float dmin = INFINITY;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const float4 ca = *reinterpret_cast<const float4*>(cs_smem + c * 32 + 8 * g);
+                  const float4 cb4 = *reinterpret_cast<const float4*>(cs_smem + c * 32 + 8 * g + 4);
+                  const float d0 = fmaf(-__uint_as_float(v[8 * g + 0]), ca.x, thr_s);
+                  const float d1 = fmaf(-__uint_as_float(v[8 * g + 1]), ca.y, thr_s);
+                  const float d2 = fmaf(-__uint_as_float(v[8 * g + 2]), ca.z, thr_s);
+                  const float d3 = fmaf(-__uint_as_float(v[8 * g + 3]), ca.w, thr_s);
+                  const float d4 = fmaf(-__uint_as_float(v[8 * g + 4]), cb4.x, thr_s);
+                  const float d5 = fmaf(-__uint_as_float(v[8 * g + 5]), cb4.y, thr_s);
+                  const float d6 = fmaf(-__uint_as_float(v[8 * g + 6]), cb4.z, thr_s);
+                  const float d7 = fmaf(-__uint_as_float(v[8 * g + 7]), cb4.w, thr_s);
+                  dmin = fminf(fminf(dmin, fminf(fminf(d0, d1), d2)), fminf(fminf(fminf(d3, d4), d5), fminf(d6, d7)));
+                }
+                hit = dmin < 0.0f;
+              } else {
+                float vmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  vmax = fmaxf(fmaxf(vmax, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1]))),
+                               fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                hit = vmax > thr;
+              }
+              if (!__any_sync(full, hit)) return 0u;
+            }
             uint32_t mq[4] = {0u, 0u, 0u, 0u};
             if (has_scale) {  // warp-uniform: two straight-line bodies, not per-score predication
 #pragma unroll
@@ -590,7 +623,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const uint32_t m = mq[0] | (mq[1] << 8) | (mq[2] << 16) | (mq[3] << 24);
-            const int lim = n_valid - c * 32;  // columns >= lim are padding
             return lim >= 32 ? m : (m & ((1u << lim) - 1u));
           };
           auto append_and_cut = [&](const uint32_t (&v)[32], uint32_t m, int c) {
