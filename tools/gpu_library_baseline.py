@@ -72,6 +72,27 @@ print(json.dumps({"what": "torch.matmul + torch.topk per chunk + merge (library 
 ms, mhz = clocks_run(lambda: lr.flatip_topk(q, corpus, k), a.steps)
 print(json.dumps({"what": "lr_flatip_topk (fused tcgen05 GEMM + top-k, this repo)", "ms": round(ms, 1), "qps": round(Q / ms * 1e3, 1),
                   "tflops": round(flops / ms / 1e9, 1), "sm_mhz": mhz}), flush=True)
-rs, ri = torch_step()
+# Identity of the results: against an fp32 top-k of the same bf16 values on 64 sampled rows.  (Round 1 compared with the
+# library step above, whose score matrix is ROUNDED TO BF16 by cuBLAS before the top-k: ~8 bits of mantissa over 8.8M
+# scores tie by the thousand, torch.topk breaks the ties by position in its own order, and only 22 % of the ids
+# coincided — a property of that baseline's rounding, not of either result.  The comparison that means something scores
+# in fp32.)
 s, i = lr.flatip_topk(q, corpus, k)
-print(json.dumps({"ids_identical_to_library_baseline": float((ri == i).float().mean())}), flush=True)
+rows = torch.linspace(0, Q - 1, 64).long().cuda()
+best_s = best_i = None
+for c0 in range(0, N, a.chunk):
+    sc = q[rows].float() @ corpus[c0:c0 + a.chunk].float().T
+    ts, ti = torch.topk(sc, k, dim=1)
+    ti += c0
+    if best_s is None:
+        best_s, best_i = ts, ti
+    else:
+        cs, ci = torch.cat([best_s, ts], 1), torch.cat([best_i, ti], 1)
+        best_s, mi = torch.topk(cs, k, dim=1)
+        best_i = torch.gather(ci, 1, mi)
+same = (best_i == i[rows])
+band = 1e-2 * best_s[:, -1:].abs()
+outside = same | ((best_s - best_s[:, -1:]).abs() <= band)   # a differing id is allowed only inside the tie band of s_k
+print(json.dumps({"rows": 64, "ids_identical_to_fp32_topk": float(same.float().mean()),
+                  "ids_identical_outside_tie_band": bool(outside.all()),
+                  "max_rel_score_err": float(((s[rows] - best_s).abs() / best_s.abs().clamp_min(1e-12)).max())}), flush=True)
