@@ -57,6 +57,9 @@ DENSE = {
     "c3m256":  (128256, 4096, 8_800_000, 10_000, 100,  256,  128002, 0),
     "c3m512":  (128256, 4096, 8_800_000, 10_000, 100,  512,  128002, 0),
     "c3m1024": (128256, 4096, 8_800_000, 10_000, 100,  1024, 128002, 0),
+    # the same widths over a corpus STORED compact [N, m] (what encoding with dense_shrink_dim = m gives): no column scales
+    "c3m128c": (128256, 4096, 8_800_000, 10_000, 100,  128,  128002, 0),
+    "c3m256c": (128256, 4096, 8_800_000, 10_000, 100,  256,  128002, 0),
     "c5b1":    (152064, 3584, 8_800_000, 1,      100,  None, 152063, 100),
     "c5b32":   (152064, 3584, 8_800_000, 32,     100,  None, 152063, 100),
 }
@@ -182,11 +185,12 @@ class DenseWorkload:
         self.Q = args.queries or Q
         self.k = args.topk or k
         self.m = m
+        self.compact = name.endswith("c") and m is not None   # corpus rows hold only the (re-normalised) MRL prefix
         self.requests_per_step = rps           # > 0: online-serving config, a step = that many requests
         self.n_batches = 4
         self.units_per_step = self.Q * (rps or 1)
         self.parity_rows = args.parity_rows
-        width = f"MRL prefix m={m} of " if m else ""
+        width = (f"compact MRL rows m={m}, table " if self.compact else f"MRL prefix m={m} of ") if m else ""
         self.metric = f"QPS (EmbBag encode + exact top-{self.k}, {self.N / 1e6:.3g}M x {width}{self.d} bf16)"
         if name == "c2" and (self.d, self.N, self.Q, self.k) == (4096, 8_800_000, 10_000, 100):
             self.metric = "QPS (EmbBag encode + exact top-100, 8.8M x 4096 bf16)"  # BASELINE.json's wording
@@ -194,7 +198,8 @@ class DenseWorkload:
     # -------------------------------------------------------------------------------- description
     def config(self, world):
         c = {"workload": (f"{self.name}: EmbeddingBag(V={self.V},d={self.d},bf16) encode + exact IP top-{self.k}, "
-                          f"{self.Q}-query batches vs {self.N}-doc bf16 corpus" + (f", MRL width {self.m}" if self.m else "")),
+                          f"{self.Q}-query batches vs {self.N}-doc bf16 corpus" + (f", MRL width {self.m}" if self.m else "")
+                          + (" (corpus stored compact [N, m], unit rows)" if self.compact else "")),
              "queries_per_step": self.units_per_step, "docs": self.N, "dim": self.d, "k": self.k,
              "max_query_tokens": MAX_TOK, "sharding": f"corpus row-sharded over {world} GPU(s)",
              "l2": "inputs larger than L2 (corpus shard streams from HBM every step)"}
@@ -218,17 +223,21 @@ class DenseWorkload:
         self.bag = lr.B200EmbeddingBag.from_pretrained(table, padding_idx=self.pad)
         self.lo, self.hi = shard_range(self.N, rank, world)
         n_local = self.hi - self.lo
-        self.corpus = torch.empty((n_local, self.d), dtype=torch.bfloat16, device=dev)
-        self.c_scale = torch.empty(n_local, dtype=torch.float32, device=dev) if self.m else None
+        self.corpus = torch.empty((n_local, self.m if self.compact else self.d), dtype=torch.bfloat16, device=dev)
+        self.c_scale = torch.empty(n_local, dtype=torch.float32, device=dev) if (self.m and not self.compact) else None
         for c0 in range((self.lo // CHUNK_ROWS) * CHUNK_ROWS, self.hi, CHUNK_ROWS):
             gc = torch.Generator(device=dev).manual_seed(1000 + c0 // CHUNK_ROWS)  # chunk-seeded: every N sees the same corpus
             blk = torch.nn.functional.normalize(torch.randn(CHUNK_ROWS, self.d, generator=gc, device=dev), dim=-1).bfloat16()
             a, b = max(c0, self.lo), min(c0 + CHUNK_ROWS, self.hi)
+            if self.compact:  # truncate, then normalise (modeling_hybrid.py:487-490), store the prefix only
+                self.corpus[a - self.lo:b - self.lo] = torch.nn.functional.normalize(blk[a - c0:b - c0, :self.m].float(), dim=-1).bfloat16()
+                del blk
+                continue
             self.corpus[a - self.lo:b - self.lo] = blk[a - c0:b - c0]
             if self.m:  # reciprocal prefix norms of the stored bf16 values (modeling_hybrid.py:487-490: truncate, then normalise)
                 self.c_scale[a - self.lo:b - self.lo] = 1.0 / blk[a - c0:b - c0, :self.m].float().norm(dim=1).clamp_min(1e-12)
             del blk
-        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if n_local * self.d * 2 < (256 << 20) else None
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if self.corpus.numel() * 2 < (256 << 20) else None
         self.host_batches = []
         for i in range(self.n_batches):
             ids, offs = make_queries(self.Q, 100 + i, self.V, self.pad)
@@ -251,9 +260,10 @@ class DenseWorkload:
 
     def search(self, qv):
         lr = self.lr
+        d_used = None if self.compact else self.m
         if self.world == 1:
-            return lr.flatip_topk(qv, self.corpus, self.k, d_used=self.m, c_scale=self.c_scale, id_offset=self.lo)
-        keys = lr.flatip_topk_sharded(qv, self.corpus, self.k, self.world, self._merge_across, d_used=self.m,
+            return lr.flatip_topk(qv, self.corpus, self.k, d_used=d_used, c_scale=self.c_scale, id_offset=self.lo)
+        keys = lr.flatip_topk_sharded(qv, self.corpus, self.k, self.world, self._merge_across, d_used=d_used,
                                       c_scale=self.c_scale, id_offset=self.lo)[2]                      # K2 on the shard
         from lightretriever_b200.sharded import exchange_candidates
         return lr.topk_merge(exchange_candidates(keys), self.k)                                        # all-gather + merge
