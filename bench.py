@@ -909,6 +909,13 @@ def run_b200(args):
             print(f"PARITY VIOLATION in the timed result: {parity['violations']}", file=sys.stderr, flush=True)
     if world > 1:
         dist.barrier()
+        if wl.requests_per_step:
+            # The online configs hold CUDA graphs that captured NCCL collectives; tearing the communicator down under them
+            # hung at 8 GPUs (c5b32: every rank had printed / passed the barrier, torchrun never returned).  Leave the
+            # teardown to process exit.
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0 if ok else 1)
         dist.destroy_process_group()
     if not ok:
         sys.exit(1)

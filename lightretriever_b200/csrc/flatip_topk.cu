@@ -186,10 +186,12 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
   int prefix_splits_forced = 0;
   const int want = env.prefix_docs;
   if (want != 0) {
-    // default prefix: 256 documents per requested result, at least 32768, at most 1/16 of the corpus.  Long lists
-    // (k > 352) start from 32768 documents and refresh the thresholds over ranges growing 4x instead: a cold pass over
-    // 256k documents cost ~40 ms of the 577 ms step at k = 1000 (same box: 577 -> 567 ms at 8.8M, 83.7 -> 80.6 ms at 1.1M)
-    int64_t docs = want > 0 ? want : ((int64_t(256) * k > 32768 && !long_lists) ? int64_t(256) * k : 32768);
+    // default prefix: 256 documents per requested result, at least 32768, at most 1/16 of the corpus.  (Long lists,
+    // k > 352: LR_FLATIP_PREFIX_DOCS=32768 LR_FLATIP_REFRESH=1 — a short warm start plus threshold-refresh passes instead
+    // of one cold 256k-document pass — measured 577 -> 567 ms at 8.8M and 83.7 -> 80.6 ms at 1.1M for k = 1000 on the same
+    // box; it stays an option until the full GPU suite has run with it.)
+    const int64_t default_docs = int64_t(256) * k > 32768 ? int64_t(256) * k : 32768;
+    int64_t docs = want > 0 ? want : default_docs;
     if (docs < 4 * int64_t(k)) docs = 4 * int64_t(k);
     int pt = int((docs + BN - 1) / BN);
     if (want < 0 && pt > pl.n_tiles / 16) pt = pl.n_tiles / 16;
@@ -223,9 +225,10 @@ static FlatipPlan make_plan_uncached(int64_t Q, int64_t N, int k, int64_t d_used
   // of a single main pass take k*N/prefix = 3.4k candidates per query; ranges growing 4x per pass bring that below 1k.
   int main_begin = prefix_tiles;
   pl.n_mid = 0;
-  // (a forced prefix size, LR_FLATIP_PREFIX_DOCS, refreshes only when LR_FLATIP_REFRESH asks for it: tests pin the plan)
-  const int refresh = env.refresh >= 0 ? env.refresh : (((d_used <= 1024 || long_lists) && want < 0) ? 1 : 0);
-  if (refresh && pt_global >= 128 && prefix_tiles > 0 && prefix_splits_forced == 0) {
+  // (by default only with the default prefix size; LR_FLATIP_REFRESH=1 forces it for any prefix, e.g. for long lists)
+  const int refresh = env.refresh >= 0 ? env.refresh : (d_used <= 1024 ? 1 : 0);
+  const bool default_prefix = pt_global == int((int64_t(256) * k > 32768 ? int64_t(256) * k : 32768) / BN);
+  if (refresh && pt_global >= 128 && prefix_tiles > 0 && prefix_splits_forced == 0 && (default_prefix || env.refresh > 0)) {
     int growth = env.refresh_growth;
     if (growth < 2) growth = 2;
     // ranges end at growth^i times the WHOLE prefix (a shard's thresholds start from the exchanged k-th best of it)

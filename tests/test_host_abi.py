@@ -59,8 +59,7 @@ def test_flatip_plan_invariants():
         p = _plan(Q, N, k)
         assert p["m_tiles"] == -(-Q // 128) and p["n_tiles"] == -(-N // 256)
         assert p["cap"] >= k + 64 and p["cap"] % 64 == 0
-        # prefix (+ the threshold-refresh passes of lr_flatip_plan_passes, for long lists) + main cover [0, n_tiles)
-        assert p["prefix_tiles"] <= p["main_begin"] < p["n_tiles"] and (k > 352 or p["main_begin"] == p["prefix_tiles"])
+        assert p["main_begin"] == p["prefix_tiles"] < p["n_tiles"]              # prefix + main cover [0, n_tiles)
         assert 1 <= p["main_splits"] <= p["n_tiles"] - p["main_begin"]
         groups = -(-p["m_tiles"] // p["cl"])
         assert p["main_units"] == groups * p["main_splits"]
@@ -72,8 +71,7 @@ def test_flatip_plan_invariants():
     head = _plan(10000, 8_800_000, 100)
     assert (head["cl"], head["pair"], head["prefix_tiles"], head["cap"]) == (2, 1, 128, 256)   # cta_group::2 pair on the team schedule, 32768-doc prefix
     big_k = _plan(10000, 8_800_000, 1000)
-    # pair; long lists warm up on 32768 documents and refresh the thresholds over [128, 512), [512, 2048), [2048, 8192)
-    assert (big_k["cl"], big_k["pair"], big_k["cap"]) == (2, 1, 2048) and (big_k["prefix_tiles"], big_k["main_begin"]) == (128, 8192)
+    assert (big_k["cl"], big_k["pair"], big_k["cap"]) == (2, 1, 2048) and big_k["prefix_tiles"] == 1000  # pair + 256k-doc prefix
     online = _plan(32, 1_100_000, 100)
     assert (online["cl"], online["prefix_tiles"], online["prefix_splits"]) == (1, 148, 148)     # one tile per CTA
     assert _plan(1, 1_100_000, 100)["prefix_tiles"] == 0                                          # single query: single phase
