@@ -1,6 +1,8 @@
 """Digest of an .ncu-rep: headline metrics, warp-stall breakdown, and instructions / stall samples per SOURCE LINE
 (the SASS page of the report joined with `nvdisasm -g` line info of the same object; build with -lineinfo).
-Usage: python tools/ncu_digest.py file.ncu-rep [object.o kernel_name_substring [top_n]]"""
+Usage: python tools/ncu_digest.py file.ncu-rep [object.o kernel_name_substring [top_n [source_root]]]
+(object.o and source_root must be the build the capture was taken from: for an older capture, check that commit out into
+a scratch worktree, compile the one .cu with -lineinfo and pass both)"""
 import collections
 import csv
 import io
@@ -14,6 +16,7 @@ rep = sys.argv[1]
 obj = sys.argv[2] if len(sys.argv) > 2 else None
 kname = sys.argv[3] if len(sys.argv) > 3 else None
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+src_root = sys.argv[5] if len(sys.argv) > 5 else os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -94,7 +97,7 @@ if obj and kname:
     for key, (s, ie, stl) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
         f, l = key
         if f not in srcs:
-            p = next((os.path.join(dp, f) for dp, _, fs in os.walk(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) if f in fs), None)
+            p = next((os.path.join(dp, f) for dp, _, fs in os.walk(src_root) if f in fs), None)
             srcs[f] = open(p).read().splitlines() if p else []
         text = srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
         top = ",".join(f"{k.replace('stall_', '')}:{v / max(s, 1):.2f}" for k, v in stl.most_common(2))
