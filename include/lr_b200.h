@@ -209,6 +209,8 @@ int lr_sparse_head_max(const void* hidden, const void* W, const float* bias, con
  * (device, 256-byte aligned, >= lr_sparse_head_packed_workspace_bytes(T, V)).  A document without a token gives
  * finfo(bf16).min before relu, as above. */
 size_t lr_sparse_head_packed_workspace_bytes(int64_t T, int64_t V);
+/* planner introspection (host only): out[4] = 256-token tiles, splits, edge-buffer offset, workspace bytes */
+int lr_sparse_head_packed_plan(int64_t T, int64_t V, int64_t* out);
 int lr_sparse_head_max_packed(const void* hidden, const void* W, const float* bias, const int32_t* cu_seqlens,
                               int64_t B, int64_t T, int64_t d, int64_t V, int relu, int log1p,
                               float* out /*[B,V]*/, void* workspace, size_t ws_bytes, void* stream);
@@ -252,6 +254,11 @@ int    lr_sparse_block_docs(void);
 int    lr_sparse_build_blockptr(const int64_t* post_indptr, const int32_t* post_doc, int64_t V, int64_t N,
                                 uint32_t* blockptr /* [V*(nblk+1)] */, void* stream);
 size_t lr_sparse_score_workspace_bytes(int64_t Q, int64_t N, int k);
+/* planner introspection (host only): out[16] = block_docs, index blocks, list capacity, flat kernel launched, row
+ * kernel launched, splits (flat), splits (rows), lists per query, workers per CTA of the four launches (flat 16-bit,
+ * flat int32, rows 16-bit, rows 32-bit), dynamic shared memory of the flat / row 16-bit launches, workspace bytes,
+ * documents per step of the row kernel */
+int lr_sparse_score_plan(int64_t Q, int64_t N, int k, int64_t* out);
 /* k <= 1024 */
 int lr_sparse_score_topk(const int32_t* q_indptr, const int32_t* q_tok, const int32_t* q_cnt, int64_t Q,
                          const int64_t* post_indptr, const int32_t* post_doc, const uint16_t* post_imp,

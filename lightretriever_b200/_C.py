@@ -49,6 +49,7 @@ PROTOTYPES = {
                                 _vp, _vp, _vp, _vp]),
     "lr_sparse_head_max": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "lr_sparse_head_packed_workspace_bytes": (_sz, [_i64, _i64]),
+    "lr_sparse_head_packed_plan": (_i32, [_i64, _i64, _vp]),
     "lr_sparse_head_max_packed": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "lr_top_p_filter": (_i32, [_vp, _i64, _i64, _f32, _i32, _vp]),
     "lr_pack_tokens": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
@@ -57,6 +58,7 @@ PROTOTYPES = {
     "lr_sparse_block_docs": (_i32, []),
     "lr_sparse_build_blockptr": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "lr_sparse_score_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "lr_sparse_score_plan": (_i32, [_i64, _i64, _i32, _vp]),
     "lr_sparse_score_topk": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

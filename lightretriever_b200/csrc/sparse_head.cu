@@ -547,6 +547,14 @@ extern "C" int lr_sparse_head_max(const void* hidden, const void* W, const float
                             static_cast<cudaStream_t>(stream));
 }
 
+// Planner introspection (host only; CPU tests): out[4] = 256-token tiles, splits, edge-buffer offset, workspace bytes
+extern "C" int lr_sparse_head_packed_plan(int64_t T, int64_t V, int64_t* out) {
+  LR_CHECK_ARG(out && T >= 1 && V >= 1, "sparse_head_packed_plan: bad arguments");
+  const PackedPlan pp = packed_plan(T, V);
+  out[0] = pp.n_tiles; out[1] = pp.splits; out[2] = int64_t(pp.off_edge); out[3] = int64_t(pp.total_bytes);
+  return LR_OK;
+}
+
 extern "C" size_t lr_sparse_head_packed_workspace_bytes(int64_t T, int64_t V) {
   if (T < 1 || V < 1) return 0;
   return packed_plan(T, V).total_bytes;

@@ -570,6 +570,24 @@ extern "C" int lr_sparse_build_blockptr(const int64_t* post_indptr, const int32_
   return LR_OK;
 }
 
+// Planner introspection (host only; CPU tests): out[16] = block_docs, index blocks, list capacity, flat kernel launched,
+// row kernel launched, splits of the flat kernel, splits of the row kernel, lists per query, workers per CTA and dynamic
+// shared memory of the flat 16-bit / flat int32 / row 16-bit / row 32-bit launches (4 x 2), workspace bytes, step docs
+extern "C" int lr_sparse_score_plan(int64_t Q, int64_t N, int k, int64_t* out) {
+  LR_CHECK_ARG(out && Q >= 1 && N >= 1 && k >= 1, "sparse_score_plan: bad arguments");
+  const SSPlan pl = ss_plan(Q, N, k);
+  int i = 0;
+  out[i++] = pl.bd; out[i++] = pl.nblk; out[i++] = pl.cap; out[i++] = pl.flat; out[i++] = pl.rows;
+  out[i++] = pl.S_flat; out[i++] = pl.S_rows; out[i++] = pl.S;
+  for (int m = 0; m < 4; ++m) {
+    out[i++] = pl.warps[m];
+  }
+  for (int m = 0; m < 2; ++m) out[i++] = int64_t(pl.smem[m * 2]);  // flat 16-bit, row 16-bit
+  out[i++] = int64_t(pl.total_bytes);
+  out[i++] = pl.acc_bytes / 2;
+  return LR_OK;
+}
+
 extern "C" size_t lr_sparse_score_workspace_bytes(int64_t Q, int64_t N, int k) {
   if (Q < 1 || N < 1 || k < 1) return 0;
   return ss_plan(Q, N, k).total_bytes;

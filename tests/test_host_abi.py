@@ -79,6 +79,55 @@ def test_flatip_plan_invariants():
     assert head["main_units"] / (head["rounds"] * head["n_clusters"]) > 0.97
 
 
+def test_sparse_score_plan_invariants():
+    """Host planner of K4 (csrc/sparse_score.cu:ss_plan): both kernels are planned (regime dispatch), every launch fits the
+    227 KB of shared memory, a unit of the row kernel keeps >= 4 steps unless the corpus is smaller, the merge sees at
+    most 64 lists per query, and the workspace the planner reports is the one the entry point asks for."""
+    import ctypes
+    lib = _C.load()
+    names = ["bd", "nblk", "cap", "flat", "rows", "S_flat", "S_rows", "S", "w_flat16", "w_flat32", "w_rows16", "w_rows32",
+             "smem_flat16", "smem_rows16", "ws", "step_docs"]
+    for Q, N, k in [(10000, 1_100_000, 100), (10000, 8_800_000, 100), (32, 1_100_000, 100), (1, 8_800_000, 1000),
+                    (20, 3000, 10), (10000, 1_100_000, 1000), (7, 50, 1024)]:
+        out = (ctypes.c_int64 * 16)()
+        assert lib.lr_sparse_score_plan(Q, N, k, out) == 0
+        p = dict(zip(names, list(out)))
+        assert p["bd"] == lib.lr_sparse_block_docs() and p["nblk"] == -(-N // p["bd"])
+        assert p["cap"] >= k + 128 and p["cap"] % 32 == 0
+        assert p["flat"] == 1 and p["rows"] == 1                                   # default: both, chosen on the device
+        assert 1 <= p["S_flat"] <= min(64, p["nblk"]) and 1 <= p["S_rows"] <= min(64, p["nblk"])
+        assert p["S"] == max(p["S_flat"], p["S_rows"])
+        assert all(1 <= p[w] <= 20 for w in ("w_flat16", "w_flat32")) and all(1 <= p[w] <= 11 for w in ("w_rows16", "w_rows32"))
+        assert 0 < p["smem_flat16"] <= 227 * 1024 and 0 < p["smem_rows16"] <= 227 * 1024
+        assert p["step_docs"] % p["bd"] == 0 and p["step_docs"] >= p["bd"]
+        steps = -(-N // p["step_docs"])
+        assert p["S_rows"] >= min(64, p["nblk"], steps // 4)                       # slices small enough to stay in L2
+        assert p["ws"] == lib.lr_sparse_score_workspace_bytes(Q, N, k) and p["ws"] % 256 == 0
+        assert p["ws"] >= p["S"] * Q * p["cap"] * 8
+    big = (ctypes.c_int64 * 16)()
+    lib.lr_sparse_score_plan(10000, 1_100_000, 100, big)
+    assert dict(zip(names, list(big)))["S_rows"] == 33 and dict(zip(names, list(big)))["w_rows16"] == 11
+
+
+def test_sparse_head_packed_plan_invariants():
+    """Host planner of the packed K3 kernel (csrc/sparse_head.cu:packed_plan): balanced runs of whole 256-token tiles, about
+    two tiles per split and at most 64 splits, every split non-empty, workspace = counters + split table + edge rows."""
+    import ctypes
+    lib = _C.load()
+    V = 128256
+    for T in (1, 255, 256, 257, 5000, 17_000, 67_500, 1_000_000):
+        out = (ctypes.c_int64 * 4)()
+        assert lib.lr_sparse_head_packed_plan(T, V, out) == 0
+        tiles, splits, off_edge, ws = list(out)
+        assert tiles == -(-T // 256) and 1 <= splits <= min(64, tiles)
+        assert splits == -(-tiles // max(2, -(-tiles // 64)))                       # ~2 tiles per split, more when T is large
+        sizes = [((s + 1) * tiles) // splits - (s * tiles) // splits for s in range(splits)]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1 and sum(sizes) == tiles
+        assert ws == lib.lr_sparse_head_packed_workspace_bytes(T, V) == off_edge + splits * 2 * V * 4
+        assert off_edge % 256 == 0 and off_edge >= 64 * 1024 + splits * 4
+    assert lib.lr_sparse_head_packed_workspace_bytes(0, V) == 0
+
+
 def test_argument_errors_map_to_value_error():
     lib = _C.load()
     rc = lib.lr_flatip_topk(None, 0, None, 0, 1, 1, 8, None, None, 0, 1, None, None, None, None, 0, None)
